@@ -1,0 +1,93 @@
+"""Lowering pass: a `NavigationProblem` (flow-field expression tree, obstacles, penalty, wrappers) -> the flat
+structures of include/dabry_b200.h.  Arbitrary Python subclasses cannot run on the device: anything outside the
+supported set raises `LoweringError` (no silent CPU evaluation)."""
+import ctypes as C
+
+import numpy as np
+
+from dabry_b200 import _native as nat
+from dabry_b200.flowfield import DiscreteFF, WrapperFF, LoweringError, FlowField
+from dabry_b200.misc import Coords
+
+
+def unwrap_flow(ff):
+    """(wrapper struct, inner field) of `ff`; identity wrapper when `ff` is not a WrapperFF."""
+    w = nat.Wrapper(0., 1., 1., (0., 0.), 1., 1.)
+    if isinstance(ff, WrapperFF):
+        w = nat.Wrapper(float(ff.time_origin), float(ff.scale_time), float(ff.scale_length),
+                        (float(ff.bl[0]), float(ff.bl[1])), float(ff._scaler_speed), float(ff._scaler_dspeed))
+        ff = ff.ff
+        if isinstance(ff, WrapperFF):
+            raise LoweringError('nested WrapperFF is not supported on the device')
+    return w, ff
+
+
+def apply_flow(handle, ff):
+    """Upload the flow field of a problem into a native handle."""
+    wrapper, inner = unwrap_flow(ff)
+    if isinstance(inner, DiscreteFF):
+        values = nat.f64(inner.values)
+        unsteady = values.ndim == 4
+        nt = values.shape[0] if unsteady else 1
+        nx, ny = values.shape[-3], values.shape[-2]
+        # host-supplied Jacobian samples (DiscreteFF.from_ff) are uploaded; the default central differences
+        # (flowfield.py:474-504) are recomputed on the device instead of being shipped
+        grad = None
+        if inner.grad_values is not None and not getattr(inner, '_grad_is_default', False):
+            grad = nat.f64(inner.grad_values)
+        b = np.asarray(inner.bounds, dtype=float)
+        lo = nat.f64(np.concatenate(((0.,), b[:, 0])) if not unsteady else b[:, 0])
+        hi = nat.f64(np.concatenate(((0.,), b[:, 1])) if not unsteady else b[:, 1])
+        handle.call('dabry_set_flow_grid', nat.dptr(values), nat.dptr(grad), nt, nx, ny, 1 if unsteady else 0,
+                    nat.dptr(lo), nat.dptr(hi), C.byref(wrapper))
+        return
+    if not isinstance(inner, FlowField):
+        raise LoweringError(f'{type(inner).__name__} is not a FlowField')
+    leaves = inner.lower()
+    arr = (nat.Leaf * len(leaves))()
+    tables = []
+    offset = 0
+    for i, leaf in enumerate(leaves):
+        arr[i].kind = leaf.kind
+        arr[i].coeff = leaf.coeff
+        arr[i].t_start = leaf.t_start
+        arr[i].t_end = leaf.t_end
+        for k, v in enumerate(leaf.params):
+            arr[i].p[k] = v
+        if leaf.table is not None:
+            if leaf.table.shape[1] != 4:
+                raise LoweringError('leaf time tables have 4 columns')
+            arr[i].nt = leaf.table.shape[0]
+            arr[i].table_off = offset
+            tables.append(leaf.table.reshape(-1))
+            offset += leaf.table.size
+    table = nat.f64(np.concatenate(tables)) if tables else None
+    handle.call('dabry_set_flow_program', arr, len(leaves), nat.dptr(table), offset, C.byref(wrapper))
+
+
+def apply_obstacles(handle, obstacles):
+    arr = (nat.Obstacle * max(len(obstacles), 1))()
+    for i, obs in enumerate(obstacles):
+        kind, scale, bl, params = obs.lower()
+        arr[i].kind = kind
+        arr[i].scale_length = scale
+        arr[i].bl[0], arr[i].bl[1] = bl
+        for k, v in enumerate(params):
+            arr[i].p[k] = v
+    handle.call('dabry_set_obstacles', arr, len(obstacles))
+
+
+def apply_penalty(handle, penalty):
+    d = penalty.lower()
+    pen = nat.Penalty()
+    pen.kind = d['kind']
+    pen.time_origin, pen.scale_time, pen.scale_length = d['time_origin'], d['scale_time'], d['scale_length']
+    pen.bl[0], pen.bl[1] = d['bl']
+    pen.scaler, pen.dx = d['scaler'], d['dx']
+    for k, v in enumerate(d['params']):
+        pen.p[k] = v
+    handle.call('dabry_set_penalty', C.byref(pen))
+
+
+def coords_code(coords):
+    return nat.GCS if coords == Coords.GCS else nat.CARTESIAN

@@ -1,0 +1,198 @@
+// extern "C" entry points of include/dabry_b200.h over Engine<DABRY_BACKEND>.
+// Included once by dabry_b200.cu (DABRY_BACKEND = CudaBackend: the product library) and once by
+// tests/hostsim/hostsim.cpp (DABRY_BACKEND = SerialBackend: g++-built test double, never shipped in the package).
+#ifndef DABRY_BACKEND
+#error "define DABRY_BACKEND before including capi.inl"
+#endif
+
+struct dabry_solver {
+    dabry::Engine<DABRY_BACKEND>* eng;
+};
+
+static thread_local std::string g_create_error;
+
+#define DABRY_GUARD(h)                 \
+    if (!(h) || !(h)->eng) return DABRY_ERR_INVALID; \
+    dabry::Engine<DABRY_BACKEND>& E = *(h)->eng
+
+extern "C" {
+
+int dabry_abi_version(void) { return DABRY_ABI_VERSION; }
+
+const char* dabry_backend_name(void) { return DABRY_BACKEND::name(); }
+
+int dabry_create(const dabry_config* c, dabry_solver** out) {
+    if (!c || !out) return DABRY_ERR_INVALID;
+    *out = nullptr;
+    if (c->abi_version != DABRY_ABI_VERSION) {
+        g_create_error = "dabry_config.abi_version mismatch";
+        return DABRY_ERR_INVALID;
+    }
+    if (c->n_time < 2 || !c->times || c->n_roots < 1 || c->max_depth < 0 || c->max_depth > 40 ||
+        c->cost_map_nx < 2 || c->cost_map_ny < 2 || c->n_index_per_subframe < 1) {
+        g_create_error = "dabry_config: need n_time >= 2, times, n_roots >= 1, 0 <= max_depth <= 40, cost map >= 2x2";
+        return DABRY_ERR_INVALID;
+    }
+    if (c->dtype != DABRY_F64 || c->integrator != DABRY_DOPRI5_SCIPY) {
+        g_create_error = "this build implements dtype F64 with the DOPRI5_SCIPY integrator";
+        return DABRY_ERR_UNSUPPORTED;
+    }
+    dabry::Engine<DABRY_BACKEND>* e = new dabry::Engine<DABRY_BACKEND>(*c);
+    if (!e->be.open(c->device)) {
+        g_create_error = e->be.error();
+        delete e;
+        return DABRY_ERR_NO_DEVICE;
+    }
+    const int rc = e->init();
+    if (rc != DABRY_OK) {
+        g_create_error = e->err;
+        delete e;
+        return rc;
+    }
+    *out = new dabry_solver{e};
+    return DABRY_OK;
+}
+
+void dabry_destroy(dabry_solver* h) {
+    if (!h) return;
+    delete h->eng;
+    delete h;
+}
+
+const char* dabry_last_error(const dabry_solver* h) {
+    if (!h || !h->eng) return g_create_error.c_str();
+    return h->eng->err.c_str();
+}
+
+int dabry_set_flow_grid(dabry_solver* h, const double* values, const double* grad, int32_t nt, int32_t nx, int32_t ny,
+                        int32_t unsteady, const double lo[3], const double hi[3], const dabry_wrapper* w) {
+    DABRY_GUARD(h);
+    if (!lo || !hi) return E.fail(DABRY_ERR_INVALID, "flow grid: bounds missing");
+    return E.set_flow_grid(values, grad, nt, nx, ny, unsteady, lo, hi, w);
+}
+
+int dabry_set_flow_program(dabry_solver* h, const dabry_leaf* leaves, int32_t n, const double* tables, int64_t n_tab,
+                           const dabry_wrapper* w) {
+    DABRY_GUARD(h);
+    if (!leaves) return E.fail(DABRY_ERR_INVALID, "flow program: leaves missing");
+    return E.set_flow_program(leaves, n, tables, n_tab, w);
+}
+
+int dabry_set_obstacles(dabry_solver* h, const dabry_obstacle* obs, int32_t n) {
+    DABRY_GUARD(h);
+    return E.set_obstacles(obs, n);
+}
+
+int dabry_set_penalty(dabry_solver* h, const dabry_penalty* pen) {
+    DABRY_GUARD(h);
+    if (!pen) return E.fail(DABRY_ERR_INVALID, "penalty missing");
+    return E.set_penalty(pen);
+}
+
+int dabry_setup(dabry_solver* h, int32_t variant, const double* costates) {
+    DABRY_GUARD(h);
+    return E.setup(variant, costates);
+}
+
+int dabry_step(dabry_solver* h) {
+    DABRY_GUARD(h);
+    return E.step();
+}
+
+int dabry_step_integrate(dabry_solver* h) {
+    DABRY_GUARD(h);
+    return E.step_integrate();
+}
+
+int dabry_step_resample(dabry_solver* h) {
+    DABRY_GUARD(h);
+    return E.step_resample();
+}
+
+int dabry_finish(dabry_solver* h) {
+    DABRY_GUARD(h);
+    return E.finish();
+}
+
+int dabry_solve(dabry_solver* h, int32_t variant, const double* costates) {
+    DABRY_GUARD(h);
+    return E.solve(variant, costates);
+}
+
+int dabry_num_sites(dabry_solver* h, int64_t* n) {
+    DABRY_GUARD(h);
+    if (!n) return DABRY_ERR_INVALID;
+    *n = E.num_sites();
+    return DABRY_OK;
+}
+
+int dabry_get_sites(dabry_solver* h, dabry_site_record* out, int64_t first, int64_t count) {
+    DABRY_GUARD(h);
+    return E.get_sites(out, first, count);
+}
+
+int dabry_get_trajs(dabry_solver* h, int64_t first, int64_t count, double* times, double* states, double* costates,
+                    double* controls, double* cost) {
+    DABRY_GUARD(h);
+    return E.get_trajs(first, count, times, states, costates, controls, cost);
+}
+
+int dabry_get_next_nb(dabry_solver* h, int64_t first, int64_t count, int32_t* next_nb) {
+    DABRY_GUARD(h);
+    return E.get_next_nb(first, count, next_nb);
+}
+
+int dabry_get_arrivals(dabry_solver* h, int64_t first, int64_t count, int32_t* index, double* cost) {
+    DABRY_GUARD(h);
+    return E.get_arrivals(first, count, index, cost);
+}
+
+int dabry_get_solution(dabry_solver* h, int64_t* site, double* cost) {
+    DABRY_GUARD(h);
+    if (site) *site = E.solution();
+    if (cost) *cost = E.solution_cost_value();
+    return DABRY_OK;
+}
+
+int dabry_get_cost_map(dabry_solver* h, int32_t full, double* out) {
+    DABRY_GUARD(h);
+    if (!out) return DABRY_ERR_INVALID;
+    return E.get_cost_map(full, out);
+}
+
+int dabry_get_stats(dabry_solver* h, dabry_stats* out) {
+    DABRY_GUARD(h);
+    if (!out) return DABRY_ERR_INVALID;
+    return E.get_stats(out);
+}
+
+int dabry_boundary_doubles(dabry_solver* h, int64_t* n) {
+    DABRY_GUARD(h);
+    if (!n) return DABRY_ERR_INVALID;
+    *n = E.boundary_doubles();
+    return DABRY_OK;
+}
+
+int dabry_export_boundary(dabry_solver* h, double* packed) {
+    DABRY_GUARD(h);
+    return E.export_boundary(packed);
+}
+
+int dabry_import_boundary(dabry_solver* h, const double* packed) {
+    DABRY_GUARD(h);
+    return E.import_boundary(packed);
+}
+
+int dabry_eval_rhs(dabry_solver* h, int64_t n, const double* t, const double* y, double* dy) {
+    DABRY_GUARD(h);
+    if (n <= 0) return DABRY_OK;
+    return E.eval_rhs(n, t, y, dy);
+}
+
+int dabry_eval_flow(dabry_solver* h, int64_t n, const double* t, const double* x, double* w, double* jac) {
+    DABRY_GUARD(h);
+    if (n <= 0) return DABRY_OK;
+    return E.eval_flow(n, t, x, w, jac);
+}
+
+}  // extern "C"

@@ -1,0 +1,308 @@
+// libdabry_b200.so - the product library: Engine<CudaBackend> behind the C ABI of include/dabry_b200.h.
+// Built for sm_100a only (nvcc -gencode arch=compute_100a,code=sm_100a).  There is no host execution path in this
+// translation unit: every phase functor runs as a CUDA kernel, one thread per extremal / site / grid node.
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include "engine.cuh"
+
+namespace dabry {
+
+// one thread per work item; the functor (problem constants, site-store pointers) travels as a __grid_constant__
+// kernel parameter so that uniform reads of the problem description hit the constant bank
+template <class F>
+__global__ void __launch_bounds__(F::kThreads) phase_kernel(int64_t n, const __grid_constant__ F f) {
+    const int64_t i = (int64_t) blockIdx.x * F::kThreads + threadIdx.x;
+    if (i < n) f(i);
+}
+
+// ---- order-preserving stream compaction (resampling insertions, trimming survivors) -----------------------
+// flags are (request >= 0).  Pass 1: warp ballot + popc gives the in-warp rank, a shuffle scan over the 32 warp
+// totals gives the in-block rank.  Pass 2: one block scans the block totals.  Pass 3: add the block base and,
+// optionally, scatter the surviving indices into a dense list.
+constexpr int kScanBlock = 1024;
+
+__global__ void __launch_bounds__(kScanBlock) scan_pass1(const int32_t* __restrict__ request, int64_t n,
+                                                         int32_t* __restrict__ offset, int32_t* __restrict__ block_sum) {
+    __shared__ int32_t warp_sum[32];
+    const int64_t i = (int64_t) blockIdx.x * kScanBlock + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool flag = i < n && request[i] >= 0;
+    const unsigned ballot = __ballot_sync(0xffffffffu, flag);
+    const int rank = __popc(ballot & ((1u << lane) - 1u));
+    if (lane == 0) warp_sum[warp] = __popc(ballot);
+    __syncthreads();
+    if (warp == 0) {
+        int v = warp_sum[lane];
+        int incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += up;
+        }
+        warp_sum[lane] = incl - v;  // exclusive
+        if (lane == 31) block_sum[blockIdx.x] = incl;
+    }
+    __syncthreads();
+    if (i < n) offset[i] = warp_sum[warp] + rank;
+}
+
+__global__ void __launch_bounds__(kScanBlock) scan_pass2(int32_t* __restrict__ block_sum, int64_t n_blocks,
+                                                         int64_t* __restrict__ total) {
+    __shared__ int32_t warp_sum[32];
+    __shared__ int32_t carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n_blocks; base += kScanBlock) {
+        const int64_t i = base + threadIdx.x;
+        const int v = i < n_blocks ? block_sum[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += up;
+        }
+        if (lane == 31) warp_sum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int w = warp_sum[lane];
+            int wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= d) wi += up;
+            }
+            warp_sum[lane] = wi - w;
+        }
+        __syncthreads();
+        const int excl = carry + warp_sum[warp] + incl - v;
+        if (i < n_blocks) block_sum[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == kScanBlock - 1) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void __launch_bounds__(kScanBlock) scan_pass3(const int32_t* __restrict__ request, int64_t n,
+                                                         int32_t* __restrict__ offset,
+                                                         const int32_t* __restrict__ block_sum,
+                                                         int32_t* __restrict__ list) {
+    const int64_t i = (int64_t) blockIdx.x * kScanBlock + threadIdx.x;
+    if (i >= n) return;
+    const int32_t o = offset[i] + block_sum[blockIdx.x];
+    offset[i] = o;
+    if (list && request[i] >= 0) list[o] = (int32_t) i;
+}
+
+// ---- arrival-time reductions (check_solutions) --------------------------------------------------------------
+__device__ __forceinline__ unsigned long long f64_order_key(double v) {  // total order of doubles as unsigned keys
+    const unsigned long long b = (unsigned long long) __double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+__global__ void __launch_bounds__(256) min_f64_kernel(const double* __restrict__ v, int64_t n,
+                                                      unsigned long long* __restrict__ out_key) {
+    unsigned long long best = ~0ull;
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) {
+        const unsigned long long k = f64_order_key(v[i]);
+        best = k < best ? k : best;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, d);
+        best = o < best ? o : best;
+    }
+    if ((threadIdx.x & 31) == 0) atomicMin(out_key, best);
+}
+
+__global__ void __launch_bounds__(256) first_equal_kernel(const double* __restrict__ v, int64_t n, double value,
+                                                          unsigned long long* __restrict__ out_index) {
+    unsigned long long best = ~0ull;
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x)
+        if (v[i] == value && (unsigned long long) i < best) best = (unsigned long long) i;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, d);
+        best = o < best ? o : best;
+    }
+    if ((threadIdx.x & 31) == 0 && best != ~0ull) atomicMin(out_index, best);
+}
+
+// ---- backend ------------------------------------------------------------------------------------------------
+class CudaBackend {
+public:
+    static const char* name() { return "cuda-sm100a"; }
+
+    ~CudaBackend() {
+        if (stream_) {
+            cudaStreamSynchronize(stream_);
+            for (cudaEvent_t e : {ev0_, ev1_, tot0_, tot1_})
+                if (e) cudaEventDestroy(e);
+            if (d_small_) cudaFree(d_small_);
+            if (d_block_sum_) cudaFree(d_block_sum_);
+            cudaStreamDestroy(stream_);
+        }
+    }
+
+    bool open(int device) {
+        int count = 0;
+        cudaError_t rc = cudaGetDeviceCount(&count);
+        if (rc != cudaSuccess || count <= 0) {
+            err_ = std::string("no CUDA device: ") + cudaGetErrorString(rc);
+            cudaGetLastError();
+            return false;
+        }
+        if (device < 0 || device >= count) {
+            err_ = "CUDA device ordinal out of range";
+            return false;
+        }
+        cudaDeviceProp prop;
+        if (!chk(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) return false;
+        if (prop.major != 10) {
+            err_ = std::string("device '") + prop.name + "' is not sm_100: this library ships sm_100a code only";
+            return false;
+        }
+        device_ = device;
+        sm_count_ = prop.multiProcessorCount;
+        if (!chk(cudaSetDevice(device), "cudaSetDevice")) return false;
+        if (!chk(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
+        cudaEventCreate(&ev0_);
+        cudaEventCreate(&ev1_);
+        cudaEventCreate(&tot0_);
+        cudaEventCreate(&tot1_);
+        if (!chk(cudaMalloc(&d_small_, 64), "cudaMalloc")) return false;
+        return true;
+    }
+
+    bool ok() const { return err_.empty(); }
+    const std::string& error() const { return err_; }
+    uint64_t launches() const { return launches_; }
+    cudaStream_t stream() const { return stream_; }
+
+    void* alloc(size_t bytes) {
+        if (bytes == 0) bytes = 8;
+        cudaSetDevice(device_);
+        void* p = nullptr;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return p;
+    }
+    template <class T>
+    void free(T* p) {
+        if (p) {
+            cudaStreamSynchronize(stream_);
+            cudaFree((void*) p);
+        }
+    }
+    void upload(void* d, const void* h, size_t bytes) {
+        chk(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, stream_), "H2D copy");
+        chk(cudaStreamSynchronize(stream_), "H2D sync");
+    }
+    void download(void* h, const void* d, size_t bytes) {
+        chk(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, stream_), "D2H copy");
+        chk(cudaStreamSynchronize(stream_), "D2H sync");
+    }
+    void zero(void* d, size_t bytes) { chk(cudaMemsetAsync(d, 0, bytes, stream_), "memset"); }
+    void copy2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows) {
+        chk(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, cudaMemcpyDeviceToDevice, stream_), "D2D copy");
+    }
+    void sync() { chk(cudaStreamSynchronize(stream_), "stream sync"); }
+
+    template <class F>
+    void launch(int64_t n, const F& f) {
+        if (n <= 0 || !ok()) return;
+        static_assert(sizeof(F) <= 4000, "phase functor must fit the kernel parameter space");
+        const int64_t blocks = (n + F::kThreads - 1) / F::kThreads;
+        phase_kernel<F><<<(unsigned) blocks, F::kThreads, 0, stream_>>>(n, f);
+        ++launches_;
+        chk(cudaGetLastError(), "kernel launch");
+    }
+
+    // exclusive prefix sum of (request >= 0) into offset; optional dense list of the flagged indices; returns total
+    int64_t scan_requests(const int32_t* request, int64_t n, int32_t* offset, int32_t* list) {
+        if (n <= 0 || !ok()) return 0;
+        const int64_t blocks = (n + kScanBlock - 1) / kScanBlock;
+        if (blocks > block_sum_cap_) {
+            if (d_block_sum_) cudaFree(d_block_sum_);
+            block_sum_cap_ = blocks + blocks / 2 + 64;
+            if (!chk(cudaMalloc(&d_block_sum_, sizeof(int32_t) * block_sum_cap_), "cudaMalloc")) return 0;
+        }
+        scan_pass1<<<(unsigned) blocks, kScanBlock, 0, stream_>>>(request, n, offset, d_block_sum_);
+        scan_pass2<<<1, kScanBlock, 0, stream_>>>(d_block_sum_, blocks, (int64_t*) d_small_);
+        scan_pass3<<<(unsigned) blocks, kScanBlock, 0, stream_>>>(request, n, offset, d_block_sum_, list);
+        launches_ += 3;
+        chk(cudaGetLastError(), "scan launch");
+        int64_t total = 0;
+        download(&total, d_small_, sizeof(total));
+        return total;
+    }
+
+    double min_f64(const double* v, int64_t n) {
+        if (n <= 0 || !ok()) return INFINITY;
+        unsigned long long key = ~0ull;
+        upload(d_small_, &key, sizeof(key));
+        const int blocks = (int) (n < 256ll * 4 * sm_count_ ? (n + 255) / 256 : 4 * sm_count_);
+        min_f64_kernel<<<blocks, 256, 0, stream_>>>(v, n, (unsigned long long*) d_small_);
+        ++launches_;
+        chk(cudaGetLastError(), "min launch");
+        download(&key, d_small_, sizeof(key));
+        const unsigned long long b = (key >> 63) ? (key & 0x7fffffffffffffffull) : ~key;
+        double out;
+        memcpy(&out, &b, sizeof(out));
+        return out;
+    }
+
+    int64_t first_equal_f64(const double* v, int64_t n, double value) {
+        if (n <= 0 || !ok()) return -1;
+        unsigned long long idx = ~0ull;
+        upload(d_small_, &idx, sizeof(idx));
+        const int blocks = (int) (n < 256ll * 4 * sm_count_ ? (n + 255) / 256 : 4 * sm_count_);
+        first_equal_kernel<<<blocks, 256, 0, stream_>>>(v, n, value, (unsigned long long*) d_small_);
+        ++launches_;
+        chk(cudaGetLastError(), "argmin launch");
+        download(&idx, d_small_, sizeof(idx));
+        return idx == ~0ull ? -1 : (int64_t) idx;
+    }
+
+    // device time of a phase: CUDA events on the launching stream
+    void tic() { cudaEventRecord(ev0_, stream_); }
+    double toc() {
+        cudaEventRecord(ev1_, stream_);
+        if (!chk(cudaEventSynchronize(ev1_), "phase sync")) return 0.;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev0_, ev1_);
+        return ms;
+    }
+    void tic_total() { cudaEventRecord(tot0_, stream_); }
+    double toc_total() {
+        cudaEventRecord(tot1_, stream_);
+        if (!chk(cudaEventSynchronize(tot1_), "solve sync")) return 0.;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, tot0_, tot1_);
+        return ms;
+    }
+
+private:
+    bool chk(cudaError_t rc, const char* what) {
+        if (rc == cudaSuccess) return true;
+        if (err_.empty()) err_ = std::string(what) + ": " + cudaGetErrorString(rc);
+        return false;
+    }
+    int device_ = 0, sm_count_ = 148;
+    cudaStream_t stream_ = nullptr;
+    cudaEvent_t ev0_ = nullptr, ev1_ = nullptr, tot0_ = nullptr, tot1_ = nullptr;
+    void* d_small_ = nullptr;
+    int32_t* d_block_sum_ = nullptr;
+    int64_t block_sum_cap_ = 0;
+    uint64_t launches_ = 0;
+    std::string err_;
+};
+
+}  // namespace dabry
+
+#define DABRY_BACKEND dabry::CudaBackend
+#include "capi.inl"

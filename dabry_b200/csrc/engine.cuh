@@ -1,0 +1,1024 @@
+// The solver loops of the reference (dabry/solver_ef.py) as a sequence of data-parallel phases over the site
+// store.  Every phase is a functor `void operator()(int64_t i)` handed to `Backend::launch(n, functor)`:
+// the product library instantiates Engine<CudaBackend> (dabry_b200.cu: one CUDA thread per i), tests/hostsim
+// instantiates Engine<SerialBackend> with g++ to step through the same source on the CPU (test infrastructure).
+//
+//   SolverEFResampling.setup / step / solve     solver_ef.py:462-470, 582-608   -> setup(), step(), solve()
+//   compute_new_sites                           solver_ef.py:630-665             -> ResamplePhase + order-preserving
+//                                                                                   compaction + SpawnPhase
+//   trim_distance                               solver_ef.py:594-600             -> TrimDistancePhase
+//   SolverEFTrimming.setup / step / trim        solver_ef.py:778-841             -> step_trimming(), trim()
+//   check_solutions                             solver_ef.py:667-685             -> finish()
+#pragma once
+#include <limits.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/dabry_b200.h"
+#include "site.cuh"
+
+namespace dabry {
+
+static_assert(sizeof(FieldLeaf) == sizeof(dabry_leaf), "leaf layout");
+static_assert(sizeof(ObstacleDesc) == sizeof(dabry_obstacle), "obstacle layout");
+static_assert(sizeof(PenaltyDesc) == sizeof(dabry_penalty), "penalty layout");
+static_assert(DABRY_MAX_TARGET_EVENTS == 4, "abi");
+
+struct Counters {  // device-resident
+    unsigned long long rk_steps, ivp_calls, spare0, spare1;
+};
+
+DABRY_HD void counter_add(unsigned long long* c, unsigned long long v) {
+#if defined(__CUDA_ARCH__)
+    atomicAdd(c, v);
+#else
+    *c += v;
+#endif
+}
+
+// ---- phases -----------------------------------------------------------------------------------------------
+
+struct FillI32Phase {
+    static constexpr int kThreads = 256;
+    int32_t* p;
+    int32_t v;
+    DABRY_HD void operator()(int64_t i) const { p[i] = v; }
+};
+
+struct FillF64Phase {
+    static constexpr int kThreads = 256;
+    double* p;
+    double v;
+    DABRY_HD void operator()(int64_t i) const { p[i] = v; }
+};
+
+// SolverEFResampling.setup (solver_ef.py:462-470): the ring of root extremals
+struct InitRootsPhase {
+    static constexpr int kThreads = 256;
+    SiteStore S;
+    const double* costates;  // [count][2] or null
+    double x0, x1, t_init, dtheta;
+    int64_t root_offset, root_count, n_roots;
+    int32_t max_depth, has_ghost;
+    DABRY_HD void operator()(int64_t i) const {
+        const int s = (int) i;
+        site_reset(S, s);
+        double p0, p1;
+        if (costates) {
+            p0 = costates[2 * i];
+            p1 = costates[2 * i + 1];
+        } else {
+            // theta = linspace(0, 2 pi, n, endpoint=False)[g] = g * (2 pi / n); costate 1000 (cos, sin) (:465-467)
+            const double th = mul_rn((double) (root_offset + i), dtheta);
+            double sn, cs;
+            sincos(th, &sn, &cs);
+            p0 = 1000. * cs;
+            p1 = 1000. * sn;
+        }
+        const int64_t o = S.at(s, 0);
+        S.xp[o] = Sample{x0, x1, p0, p1};
+        S.tt[o] = t_init;
+        S.dyadic[s] = (root_offset + i) << max_depth;
+        S.valid_first[s] = 0;
+        S.valid_last[s] = 0;
+        // ring neighbour at grid index 0 (:468-469); the last local root points at the ghost slot when the ring
+        // is sharded over several handles
+        int nb = s + 1;
+        if (i == root_count - 1) nb = has_ghost ? (int) root_count : 0;
+        S.next_nb[o] = nb;
+    }
+};
+
+struct GhostInitPhase {  // the ghost slot = ring root `ring_index`, evaluated by the same code as the local roots
+    static constexpr int kThreads = 32;
+    InitRootsPhase roots;
+    int64_t slot, ring_index;
+    DABRY_HD void operator()(int64_t) const {
+        InitRootsPhase h = roots;
+        h.costates = nullptr;
+        h.root_offset = ring_index - slot;
+        h.root_count = -1;
+        h(slot);
+        h.S.flags[slot] = SITE_GHOST;
+        h.S.next_nb[h.S.at((int) slot, 0)] = -1;
+    }
+};
+
+template <int FK>
+struct IntegratePhase {
+    static constexpr int kThreads = 128;
+    ProblemDev P;
+    SolverParams C;
+    SiteStore S;
+    const int32_t* list;  // null: sites [base, base + n)
+    int32_t base, index_t;
+    Counters* counters;
+    DABRY_HD void operator()(int64_t i) const {
+        const int s = list ? list[i] : base + (int) i;
+        unsigned attempts = 0, calls = 0;
+        site_integrate<FK>(P, C, S, s, index_t, attempts, calls);
+        counter_add(&counters->rk_steps, attempts);
+        counter_add(&counters->ivp_calls, calls);
+    }
+};
+
+struct ConnectPhase {  // connect_to_parents (solver_ef.py:690-699)
+    static constexpr int kThreads = 256;
+    SiteStore S;
+    const int32_t* list;
+    int32_t base;
+    DABRY_HD void operator()(int64_t i) const { site_connect(S, list ? list[i] : base + (int) i); }
+};
+
+struct ResamplePhase {  // compute_new_sites, one site of the loop at solver_ef.py:634-661
+    static constexpr int kThreads = 256;
+    ProblemDev P;
+    SolverParams C;
+    SiteStore S;
+    int32_t index_t_hi;
+    int32_t* request;
+    DABRY_HD void operator()(int64_t i) const {
+        const int s = (int) i;
+        request[s] = (S.flags[s] & SITE_GHOST) ? -1 : site_resample(P, C, S, s, index_t_hi);
+    }
+};
+
+struct SpawnPhase {  // site_from_parents + dict insertion order (solver_ef.py:651, 663-664)
+    static constexpr int kThreads = 256;
+    SolverParams C;
+    SiteStore S;
+    const int32_t* request;
+    const int32_t* offset;  // exclusive prefix sum of (request >= 0)
+    int32_t n_old, subframe;
+    DABRY_HD void operator()(int64_t i) const {
+        const int s = (int) i;
+        if (request[s] >= 0) site_spawn(C, S, s, n_old + offset[s], request[s], subframe);
+    }
+};
+
+struct TrimDistancePhase {
+    static constexpr int kThreads = 256;
+    ProblemDev P;
+    SolverParams C;
+    SiteStore S;
+    DABRY_HD void operator()(int64_t i) const {
+        if (!(S.flags[i] & SITE_GHOST)) site_trim_distance(P, C, S, (int) i);
+    }
+};
+
+struct ArrivalPhase {
+    static constexpr int kThreads = 256;
+    ProblemDev P;
+    SiteStore S;
+    int32_t* arr_index;
+    double* arr_cost;
+    DABRY_HD void operator()(int64_t i) const {
+        double c = 0.;
+        int k = -1;
+        if (!(S.flags[i] & SITE_GHOST)) k = site_arrival(P, S, (int) i, c);
+        arr_index[i] = k;
+        arr_cost[i] = k >= 0 ? c : INFINITY;
+    }
+};
+
+struct ValidFlagPhase {  // membership in sites_valid[subframe] (solver_ef.py:803)
+    static constexpr int kThreads = 256;
+    SiteStore S;
+    int32_t subframe;
+    int32_t* flag;
+    DABRY_HD void operator()(int64_t i) const {
+        flag[i] = (!(S.flags[i] & SITE_GHOST) && S.valid_first[i] <= subframe && subframe <= S.valid_last[i]) ? 0 : -1;
+    }
+};
+
+struct RasterPhase {  // cost_map_triangle (solver_ef.py:860-889), one (site, grid index) cell per i
+    static constexpr int kThreads = 128;
+    SolverParams C;
+    SiteStore S;
+    double* map;
+    int32_t n_sites, k_lo, k_hi;          // grid indices [k_lo, k_hi]
+    int32_t subframe, valid_a, valid_b;   // site set: created at `subframe` or valid in some sub-frame of [a, b)
+    int32_t all_sites;
+    DABRY_HD void operator()(int64_t i) const {
+        const int s = (int) (i % n_sites), k = k_lo + (int) (i / n_sites);
+        if (S.flags[s] & SITE_GHOST) return;
+        if (!all_sites) {
+            const bool member = S.created_subframe[s] == subframe ||
+                                (valid_a < valid_b && S.valid_first[s] <= valid_b - 1 && S.valid_last[s] >= valid_a);
+            if (!member) return;
+        }
+        if (k < S.index_t_init[s] || k >= S.check_next[s] || k > k_hi) return;
+        site_rasterize(C, S, map, s, k);
+    }
+};
+
+struct TrimPhase {  // SolverEFTrimming.trim, loop at solver_ef.py:831-841
+    static constexpr int kThreads = 256;
+    SolverParams C;
+    SiteStore S;
+    const double* map;
+    int32_t subframe, index;
+    DABRY_HD void operator()(int64_t i) const {
+        const int s = (int) i;
+        if (S.flags[s] & SITE_GHOST) return;
+        const bool considered = (S.valid_first[s] <= subframe && subframe <= S.valid_last[s]) ||
+                                S.created_subframe[s] == subframe;
+        if (!considered || S.closure[s] != CLOSURE_NONE) return;
+        if (site_trim(C, S, map, s, index)) {
+            if (S.valid_first[s] > S.valid_last[s]) S.valid_first[s] = subframe + 1;
+            S.valid_last[s] = subframe + 1;
+        }
+    }
+};
+
+template <int FK>
+struct EvalRhsPhase {
+    static constexpr int kThreads = 128;
+    ProblemDev P;
+    const double* t;
+    const double* y;
+    double* dy;
+    DABRY_HD void operator()(int64_t i) const { rhs_aug<FK>(P, t[i], y + 4 * i, dy + 4 * i); }
+};
+
+template <int FK>
+struct EvalFlowPhase {
+    static constexpr int kThreads = 128;
+    ProblemDev P;
+    const double* t;
+    const double* x;
+    double* w;
+    double* jac;
+    DABRY_HD void operator()(int64_t i) const {
+        Flow f;
+        field_eval<FK>(P.field, t[i], x[2 * i], x[2 * i + 1], f);
+        w[2 * i] = f.w0;
+        w[2 * i + 1] = f.w1;
+        jac[4 * i] = f.j00;
+        jac[4 * i + 1] = f.j01;
+        jac[4 * i + 2] = f.j10;
+        jac[4 * i + 3] = f.j11;
+    }
+};
+
+// DiscreteFF.compute_derivatives (flowfield.py:474-504) fused with the repack into pair records (fields.cuh).
+// One i per node (k, ix, iy) of the packed grid.
+struct PackGridPhase {
+    static constexpr int kThreads = 256;
+    const double* values;  // (nt, nx, ny, 2)
+    const double* grad;    // (nt, nx, ny, 2, 2) or null
+    double* out;           // pair records
+    int32_t nt, nx, ny;
+    double two_dx, two_dy;
+    DABRY_HD void node(int k, int ix, int iy, double* c) const {
+        const int64_t n = ((int64_t) k * nx + ix) * ny + iy;
+        c[0] = values[2 * n];
+        c[1] = values[2 * n + 1];
+        if (grad) {
+            c[2] = grad[4 * n];
+            c[3] = grad[4 * n + 1];
+            c[4] = grad[4 * n + 2];
+            c[5] = grad[4 * n + 3];
+            return;
+        }
+        // central differences at the nearest interior node: borders copy the adjacent interior line, corners the
+        // diagonal interior node (flowfield.py:487-504)
+        const int ie = iclamp(ix, 1, nx - 2), je = iclamp(iy, 1, ny - 2);
+        const int64_t xp = ((int64_t) k * nx + ie + 1) * ny + je, xm = ((int64_t) k * nx + ie - 1) * ny + je;
+        const int64_t yp = ((int64_t) k * nx + ie) * ny + je + 1, ym = ((int64_t) k * nx + ie) * ny + je - 1;
+        c[2] = (values[2 * xp] - values[2 * xm]) / two_dx;
+        c[3] = (values[2 * yp] - values[2 * ym]) / two_dy;
+        c[4] = (values[2 * xp + 1] - values[2 * xm + 1]) / two_dx;
+        c[5] = (values[2 * yp + 1] - values[2 * ym + 1]) / two_dy;
+    }
+    DABRY_HD void operator()(int64_t i) const {
+        const int iy = (int) (i % ny);
+        const int ix = (int) ((i / ny) % nx);
+        const int k = (int) (i / ((int64_t) ny * nx));
+        double a[6], b[6];
+        node(k, ix, iy, a);
+        node(imin(k + 1, nt - 1), ix, iy, b);
+        double* o = out + 12 * i;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            o[2 * c] = a[c];
+            o[2 * c + 1] = b[c];
+        }
+    }
+};
+
+struct GatherTrajPhase {  // time-major store -> per-site padded rows for the host (dabry_get_trajs)
+    static constexpr int kThreads = 256;
+    SiteStore S;
+    int64_t first;
+    int32_t n_time;
+    double* times;
+    double* states;
+    double* costates;
+    double* controls;
+    double* cost;
+    DABRY_HD void operator()(int64_t i) const {
+        const int64_t r = i / n_time;
+        const int k = (int) (i % n_time);
+        const int s = (int) (first + r);
+        const int k0 = S.index_t_init[s], n = S.n_samples[s];
+        const bool ok = k >= k0 && k < k0 + n;
+        const int64_t o = S.at(s, k);
+        const double nan = quiet_nan();
+        if (times) times[i] = ok ? S.tt[o] : nan;
+        if (states) {
+            states[2 * i] = ok ? S.xp[o].x0 : nan;
+            states[2 * i + 1] = ok ? S.xp[o].x1 : nan;
+        }
+        if (costates) {
+            costates[2 * i] = ok ? S.xp[o].p0 : nan;
+            costates[2 * i + 1] = ok ? S.xp[o].p1 : nan;
+        }
+        if (controls) {
+            controls[2 * i] = ok ? S.ctrl[o].u0 : nan;
+            controls[2 * i + 1] = ok ? S.ctrl[o].u1 : nan;
+        }
+        if (cost) cost[i] = ok ? site_cost_at(S, s, k) : nan;
+    }
+};
+
+struct GatherNbPhase {
+    static constexpr int kThreads = 256;
+    SiteStore S;
+    int64_t first;
+    int32_t n_time;
+    int32_t* out;
+    DABRY_HD void operator()(int64_t i) const {
+        out[i] = S.next_nb[S.at((int) (first + i / n_time), (int) (i % n_time))];
+    }
+};
+
+struct GatherRecordPhase {
+    static constexpr int kThreads = 256;
+    SiteStore S;
+    int64_t first;
+    dabry_site_record* out;
+    DABRY_HD void operator()(int64_t i) const {
+        const int s = (int) (first + i);
+        dabry_site_record r;
+        r.dyadic = S.dyadic[s];
+        r.index_t_init = S.index_t_init[s];
+        r.n_samples = S.n_samples[s];
+        r.closure = S.closure[s];
+        r.neuter = S.neuter[s];
+        r.index_neutered = S.index_neutered[s];
+        r.obstacle = S.obstacle[s];
+        r.index_t_obs = S.index_t_obs[s];
+        r.obs_trigo = S.trigo[s];
+        r.index_t_check_next = S.check_next[s];
+        r.depth = S.depth[s];
+        r.parent_prev = S.parent_prev[s];
+        r.parent_next = S.parent_next[s];
+        r.n_target_events = S.n_target_events[s];
+        r.ivp_status = S.ivp_status[s];
+        r.t_enter_obs = S.t_enter_obs[s];
+        r.cost0 = S.cost0[s];
+        for (int e = 0; e < DABRY_MAX_TARGET_EVENTS; ++e)
+            r.t_target_events[e] = S.t_target_events[(int64_t) s * DABRY_MAX_TARGET_EVENTS + e];
+        out[i] = r;
+    }
+};
+
+// multi-GPU ring boundary: one site <-> a packed buffer of n_time * 7 + 16 doubles
+#define DABRY_BOUNDARY_HEADER 16
+struct BoundaryPhase {
+    static constexpr int kThreads = 128;
+    SiteStore S;
+    int32_t site, do_import, n_time;
+    double* buf;
+    DABRY_HD void operator()(int64_t k) const {
+        const int64_t o = S.at(site, (int) k);
+        double* row = buf + DABRY_BOUNDARY_HEADER + 7 * k;
+        if (!do_import) {
+            row[0] = S.xp[o].x0; row[1] = S.xp[o].x1; row[2] = S.xp[o].p0; row[3] = S.xp[o].p1;
+            row[4] = S.ctrl[o].u0; row[5] = S.ctrl[o].u1; row[6] = S.tt[o];
+            if (k == 0) {
+                buf[0] = (double) S.index_t_init[site]; buf[1] = (double) S.n_samples[site];
+                buf[2] = (double) S.closure[site]; buf[3] = (double) S.obstacle[site];
+                buf[4] = (double) S.index_t_obs[site]; buf[5] = (double) S.trigo[site];
+                buf[6] = (double) S.depth[site]; buf[7] = S.cost0[site]; buf[8] = (double) S.dyadic[site];
+            }
+        } else {
+            S.xp[o] = Sample{row[0], row[1], row[2], row[3]};
+            S.ctrl[o] = Control{row[4], row[5]};
+            S.tt[o] = row[6];
+            if (k == 0) {
+                site_reset(S, site);
+                S.index_t_init[site] = (int) buf[0]; S.n_samples[site] = (int) buf[1];
+                S.closure[site] = (int) buf[2]; S.obstacle[site] = (int) buf[3];
+                S.index_t_obs[site] = (int) buf[4]; S.trigo[site] = (int) buf[5];
+                S.depth[site] = (int) buf[6]; S.cost0[site] = buf[7]; S.dyadic[site] = (int64_t) buf[8];
+                S.flags[site] = SITE_GHOST;
+                S.check_next[site] = 0;
+            }
+        }
+    }
+};
+
+// ---- engine -------------------------------------------------------------------------------------------------
+
+template <class B>
+class Engine {
+public:
+    B be;
+    dabry_config cfg;
+    ProblemDev P;
+    SolverParams C;
+    SiteStore S;
+    std::string err;
+    dabry_stats stats;
+
+    explicit Engine(const dabry_config& c) : cfg(c) {
+        memset(&P, 0, sizeof(P));
+        memset(&C, 0, sizeof(C));
+        memset(&S, 0, sizeof(S));
+        memset(&stats, 0, sizeof(stats));
+        times_h.assign(c.times, c.times + c.n_time);
+        cfg.times = nullptr;
+        P.coords = c.coords;
+        P.srf = c.srf;
+        P.x_target[0] = c.x_target[0];
+        P.x_target[1] = c.x_target[1];
+        P.target_radius_sq = c.target_radius * c.target_radius;  // ** 2 (solver_ef.py:312)
+        P.rtol = c.rtol;
+        P.atol = c.atol;
+        P.max_step = c.max_step;
+        P.field.kind = -1;
+        P.penalty.kind = PEN_NONE;
+        C.max_depth = c.max_depth;
+        C.mode_origin = c.mode_origin;
+        C.follow_obstacles = 1;
+        C.n_roots = c.n_roots;
+        C.cm_nx = c.cost_map_nx;
+        C.cm_ny = c.cost_map_ny;
+        C.max_dist_sq = c.max_dist * c.max_dist;
+        C.ff_max_norm = c.ff_max_norm;
+        for (int a = 0; a < 2; ++a) {
+            C.bl[a] = c.bl[a];
+            C.tr[a] = c.tr[a];
+        }
+    }
+
+    ~Engine() {
+        free_store(S);
+        be.free(d_times);
+        be.free(d_tables);
+        be.free(d_grid);
+        be.free(d_request);
+        be.free(d_offset);
+        be.free(d_list);
+        be.free(d_map);
+        be.free(d_arr_index);
+        be.free(d_arr_cost);
+        be.free(d_counters);
+        be.free(d_scratch);
+    }
+
+    int init() {
+        if (!be.ok()) return fail(DABRY_ERR_NO_DEVICE, be.error());
+        d_times = (double*) be.alloc(sizeof(double) * cfg.n_time);
+        be.upload(d_times, times_h.data(), sizeof(double) * cfg.n_time);
+        d_counters = (Counters*) be.alloc(sizeof(Counters));
+        be.zero(d_counters, sizeof(Counters));
+        d_map = (double*) be.alloc(sizeof(double) * C.cm_nx * C.cm_ny);
+        return check();
+    }
+
+    // ---- problem ----
+    int set_flow_grid(const double* values, const double* grad, int nt, int nx, int ny, int unsteady,
+                      const double* lo, const double* hi, const dabry_wrapper* w) {
+        if (!values || nt < 1 || nx < 3 || ny < 3 || (!unsteady && nt != 1))
+            return fail(DABRY_ERR_INVALID, "flow grid: need values, nt >= 1, nx >= 3, ny >= 3 (nt == 1 if steady)");
+        be.tic();
+        const int64_t nodes = (int64_t) nt * nx * ny;
+        double* d_values = (double*) be.alloc(sizeof(double) * 2 * nodes);
+        double* d_grad = grad ? (double*) be.alloc(sizeof(double) * 4 * nodes) : nullptr;
+        be.free(d_grid);
+        d_grid = (double*) be.alloc(sizeof(double) * 12 * nodes);
+        if (!d_values || !d_grid || (grad && !d_grad)) return fail(DABRY_ERR_CAPACITY, "flow grid: out of device memory");
+        be.upload(d_values, values, sizeof(double) * 2 * nodes);
+        if (grad) be.upload(d_grad, grad, sizeof(double) * 4 * nodes);
+        GridDesc& G = P.field.grid;
+        G.data = d_grid;
+        G.nt = nt;
+        G.nx = nx;
+        G.ny = ny;
+        G.unsteady = unsteady;
+        const int n_ax[3] = {nt, nx, ny};
+        for (int a = 0; a < 3; ++a) {
+            G.lo[a] = lo[a];
+            // (bounds[:, 1] - bounds[:, 0]) / (shape - 1)  (flowfield.py:198-199)
+            G.spacing[a] = (a == 0 && !unsteady) ? 1. : (hi[a] - lo[a]) / (double) (n_ax[a] - 1);
+        }
+        PackGridPhase ph{d_values, d_grad, d_grid, nt, nx, ny, 2 * G.spacing[1], 2 * G.spacing[2]};
+        be.launch(nodes, ph);
+        be.sync();
+        be.free(d_values);
+        be.free(d_grad);
+        P.field.kind = FIELD_GRID;
+        set_wrapper(w);
+        stats.ms_upload += be.toc();
+        return check();
+    }
+
+    int set_flow_program(const dabry_leaf* leaves, int n, const double* tables, int64_t n_tab, const dabry_wrapper* w) {
+        if (n < 1 || n > DABRY_MAX_LEAVES) return fail(DABRY_ERR_UNSUPPORTED, "flow program: 1..8 leaves supported");
+        memcpy(P.field.leaves, leaves, sizeof(dabry_leaf) * n);
+        P.field.n_leaves = n;
+        be.free(d_tables);
+        d_tables = nullptr;
+        if (n_tab > 0) {
+            d_tables = (double*) be.alloc(sizeof(double) * n_tab);
+            be.upload(d_tables, tables, sizeof(double) * n_tab);
+        }
+        P.field.tables = d_tables;
+        P.field.kind = FIELD_PROGRAM;
+        set_wrapper(w);
+        return check();
+    }
+
+    int set_obstacles(const dabry_obstacle* obs, int n) {
+        if (n < 0 || n > DABRY_MAX_OBSTACLES) return fail(DABRY_ERR_UNSUPPORTED, "at most 8 obstacles");
+        memcpy(P.obstacles, obs, sizeof(dabry_obstacle) * n);
+        P.n_obstacles = n;
+        return DABRY_OK;
+    }
+
+    int set_penalty(const dabry_penalty* pen) {
+        memcpy(&P.penalty, pen, sizeof(dabry_penalty));
+        return DABRY_OK;
+    }
+
+    // ---- solve ----
+    int setup(int variant_, const double* costates) {
+        if (P.field.kind < 0) return fail(DABRY_ERR_INVALID, "no flow field set");
+        if (cfg.root_count < 1 || cfg.root_offset < 0 || cfg.root_offset + cfg.root_count > cfg.n_roots)
+            return fail(DABRY_ERR_INVALID, "bad root range");
+        variant = variant_;
+        C.follow_obstacles = variant == DABRY_SIMPLE ? 0 : 1;
+        has_ghost = cfg.root_count < cfg.n_roots ? 1 : 0;
+        const int64_t n0 = cfg.root_count + has_ghost;
+        int64_t cap = cfg.max_sites > 0 ? cfg.max_sites : 2 * n0 + 1024;
+        if (cap < n0) cap = n0;
+        free_store(S);
+        memset(&S, 0, sizeof(S));
+        n_sites = 0;
+        if (int rc = reserve(cap)) return rc;
+        double* d_cost = nullptr;
+        if (costates) {
+            d_cost = (double*) be.alloc(sizeof(double) * 2 * cfg.root_count);
+            be.upload(d_cost, costates, sizeof(double) * 2 * cfg.root_count);
+        }
+        InitRootsPhase ph{S, d_cost, cfg.x_init[0], cfg.x_init[1], cfg.t_init, 2 * M_PI / (double) cfg.n_roots,
+                          cfg.root_offset, cfg.root_count, cfg.n_roots, cfg.max_depth, has_ghost};
+        be.launch(cfg.root_count, ph);
+        if (has_ghost) {  // placeholder until dabry_import_boundary: the un-integrated next root of the ring
+            GhostInitPhase g{ph, cfg.root_count, (cfg.root_offset + cfg.root_count) % cfg.n_roots};
+            be.launch(1, g);
+        }
+        be.sync();
+        be.free(d_cost);
+        n_sites = n0;
+        shoot_begin = 0;
+        shoot_end = (int32_t) cfg.root_count;
+        round = 0;
+        i_subframe = 0;
+        solution_site = -1;
+        solution_cost = NAN;
+        arrivals_ready = false;
+        last_new = 0;
+        be.zero(d_counters, sizeof(Counters));
+        stats.rounds = 0;
+        stats.ms_integrate = stats.ms_resample = stats.ms_trim = stats.ms_arrival = stats.ms_total = 0.;
+        return check();
+    }
+
+    int n_subframes() const {  // solver_ef.py:784-786
+        const int q = cfg.n_index_per_subframe;
+        return cfg.n_time / q + (cfg.n_time % q > 0 ? 1 : 0);
+    }
+
+    int step_integrate() {
+        if (variant == DABRY_TRIMMING) return fail(DABRY_ERR_INVALID, "step_integrate: resampling/simple only");
+        if (shoot_end > shoot_begin) {
+            if (int rc = integrate(nullptr, shoot_begin, shoot_end - shoot_begin, cfg.n_time - 1)) return rc;
+        }
+        return check();
+    }
+
+    int step_resample() {
+        shoot_begin = shoot_end = (int32_t) n_sites;
+        if (variant == DABRY_RESAMPLING) {
+            if (int rc = resample(cfg.n_time - 1, 0)) return rc;
+            be.tic();
+            if (C.ff_max_norm > 1e-8) {  // not np.isclose(max_norm, 0) (solver_ef.py:595)
+                TrimDistancePhase td{P, C, S};
+                be.launch(n_sites, td);
+            }
+            stats.ms_resample += be.toc();
+        }
+        ++round;
+        stats.rounds = round;
+        return check();
+    }
+
+    int step() {
+        if (variant == DABRY_TRIMMING) return step_trimming();
+        if (int rc = step_integrate()) return rc;
+        return step_resample();
+    }
+
+    // SolverEFTrimming.step (solver_ef.py:802-817)
+    int step_trimming() {
+        const int q = cfg.n_index_per_subframe;
+        const int next = imin((i_subframe + 1) * q, cfg.n_time);  // index_t_next_subframe (:792-794)
+        const int target = next - 1;
+        if (int rc = ensure_aux(n_sites)) return rc;
+        be.tic();
+        ValidFlagPhase vf{S, i_subframe, d_request};
+        be.launch(n_sites, vf);
+        int64_t n_list = be.scan_requests(d_request, n_sites, d_offset, d_list);
+        stats.ms_trim += be.toc();
+        const int32_t* list = d_list;
+        int32_t base = 0;
+        while (n_list > 0) {
+            if (int rc = integrate(list, base, n_list, target)) return rc;
+            if (int rc = resample(target, i_subframe)) return rc;
+            list = nullptr;
+            base = shoot_begin;
+            n_list = shoot_end - shoot_begin;
+        }
+        if (int rc = trim(target)) return rc;
+        ++i_subframe;
+        ++round;
+        stats.rounds = round;
+        return check();
+    }
+
+    int finish() {
+        if (int rc = ensure_aux(n_sites)) return rc;
+        be.tic();
+        ArrivalPhase ap{P, S, d_arr_index, d_arr_cost};
+        be.launch(n_sites, ap);
+        // warp-level min reduction of the arrival cost, then of the slot among the minimisers (lowest slot wins)
+        solution_cost = be.min_f64(d_arr_cost, n_sites);
+        solution_site = -1;
+        if (solution_cost < INFINITY) solution_site = be.first_equal_f64(d_arr_cost, n_sites, solution_cost);
+        else solution_cost = NAN;
+        arrivals_ready = true;
+        stats.ms_arrival += be.toc();
+        return check();
+    }
+
+    int solve(int variant_, const double* costates) {
+        be.tic_total();
+        if (int rc = setup(variant_, costates)) return rc;
+        if (variant == DABRY_TRIMMING) {
+            const int n = n_subframes();
+            for (int i = 0; i < n; ++i)
+                if (int rc = step_trimming()) return rc;
+        } else {
+            const int n = variant == DABRY_SIMPLE ? 1 : cfg.max_depth;
+            for (int i = 0; i < n; ++i) {
+                if (int rc = step()) return rc;
+                // the remaining rounds of the reference loop (solver_ef.py:604-605) are no-ops once a round
+                // neither integrates nor creates a site: compute_new_sites and trim_distance are idempotent
+                if (shoot_end == shoot_begin) break;
+            }
+        }
+        int rc = finish();
+        stats.ms_total = be.toc_total();
+        return rc;
+    }
+
+    // ---- results ----
+    int get_sites(dabry_site_record* out, int64_t first, int64_t count) {
+        if (first < 0 || count < 0 || first + count > n_sites) return fail(DABRY_ERR_INVALID, "site range");
+        if (count == 0) return DABRY_OK;
+        dabry_site_record* d = (dabry_site_record*) scratch(sizeof(dabry_site_record) * count);
+        if (!d) return fail(DABRY_ERR_CAPACITY, "out of device memory");
+        GatherRecordPhase ph{S, first, d};
+        be.launch(count, ph);
+        be.download(out, d, sizeof(dabry_site_record) * count);
+        return check();
+    }
+
+    int get_trajs(int64_t first, int64_t count, double* times, double* states, double* costates, double* controls,
+                  double* cost) {
+        if (first < 0 || count < 0 || first + count > n_sites) return fail(DABRY_ERR_INVALID, "site range");
+        if (count == 0) return DABRY_OK;
+        const int64_t n = count * cfg.n_time;
+        double* d = (double*) scratch(sizeof(double) * n * 8);
+        if (!d) return fail(DABRY_ERR_CAPACITY, "out of device memory");
+        GatherTrajPhase ph{S, first, cfg.n_time, times ? d : nullptr, states ? d + n : nullptr,
+                           costates ? d + 3 * n : nullptr, controls ? d + 5 * n : nullptr, cost ? d + 7 * n : nullptr};
+        be.launch(n, ph);
+        if (times) be.download(times, d, sizeof(double) * n);
+        if (states) be.download(states, d + n, sizeof(double) * 2 * n);
+        if (costates) be.download(costates, d + 3 * n, sizeof(double) * 2 * n);
+        if (controls) be.download(controls, d + 5 * n, sizeof(double) * 2 * n);
+        if (cost) be.download(cost, d + 7 * n, sizeof(double) * n);
+        return check();
+    }
+
+    int get_next_nb(int64_t first, int64_t count, int32_t* out) {
+        if (first < 0 || count < 0 || first + count > n_sites) return fail(DABRY_ERR_INVALID, "site range");
+        if (count == 0) return DABRY_OK;
+        const int64_t n = count * cfg.n_time;
+        int32_t* d = (int32_t*) scratch(sizeof(int32_t) * n);
+        if (!d) return fail(DABRY_ERR_CAPACITY, "out of device memory");
+        GatherNbPhase ph{S, first, cfg.n_time, d};
+        be.launch(n, ph);
+        be.download(out, d, sizeof(int32_t) * n);
+        return check();
+    }
+
+    int get_arrivals(int64_t first, int64_t count, int32_t* index, double* cost) {
+        if (!arrivals_ready) return fail(DABRY_ERR_INVALID, "call dabry_finish first");
+        if (first < 0 || count < 0 || first + count > n_sites) return fail(DABRY_ERR_INVALID, "site range");
+        if (index) be.download(index, d_arr_index + first, sizeof(int32_t) * count);
+        if (cost) be.download(cost, d_arr_cost + first, sizeof(double) * count);
+        return check();
+    }
+
+    int get_cost_map(int full, double* out) {
+        if (full) {
+            if (int rc = build_cost_map(0, cfg.n_time - 1, 1, 0, 0, 0)) return rc;
+        }
+        be.download(out, d_map, sizeof(double) * C.cm_nx * C.cm_ny);
+        return check();
+    }
+
+    int get_stats(dabry_stats* out) {
+        Counters c;
+        be.download(&c, d_counters, sizeof(c));
+        stats.rk_steps = c.rk_steps;
+        stats.ivp_calls = c.ivp_calls;
+        stats.rhs_evals = cfg.integrator == DABRY_RK4_FIXED ? 4 * c.rk_steps : 6 * c.rk_steps + 2 * c.ivp_calls;
+        stats.kernel_launches = be.launches();
+        stats.n_sites = n_sites - has_ghost;
+        stats.capacity = S.capacity;
+        *out = stats;
+        return check();
+    }
+
+    int64_t num_sites() const { return n_sites; }
+    int64_t solution() const { return solution_site; }
+    double solution_cost_value() const { return solution_cost; }
+
+    // ---- multi-GPU boundary ----
+    int64_t boundary_doubles() const { return (int64_t) cfg.n_time * 7 + DABRY_BOUNDARY_HEADER; }
+    int export_boundary(double* packed) {
+        const int64_t n = boundary_doubles();
+        double* d = (double*) scratch(sizeof(double) * n);
+        BoundaryPhase ph{S, 0, 0, cfg.n_time, d};
+        be.launch(cfg.n_time, ph);
+        be.download(packed, d, sizeof(double) * n);
+        return check();
+    }
+    int import_boundary(const double* packed) {
+        if (!has_ghost) return fail(DABRY_ERR_INVALID, "this handle owns the whole ring: no ghost site");
+        const int64_t n = boundary_doubles();
+        double* d = (double*) scratch(sizeof(double) * n);
+        be.upload(d, packed, sizeof(double) * n);
+        BoundaryPhase ph{S, (int32_t) cfg.root_count, 1, cfg.n_time, d};
+        be.launch(cfg.n_time, ph);
+        return check();
+    }
+
+    // ---- evaluation hooks ----
+    int eval_rhs(int64_t n, const double* t, const double* y, double* dy) {
+        if (P.field.kind < 0) return fail(DABRY_ERR_INVALID, "no flow field set");
+        double* d = (double*) scratch(sizeof(double) * n * 9);
+        if (!d) return fail(DABRY_ERR_CAPACITY, "out of device memory");
+        be.upload(d, t, sizeof(double) * n);
+        be.upload(d + n, y, sizeof(double) * 4 * n);
+        if (P.field.kind == FIELD_GRID) be.launch(n, EvalRhsPhase<FIELD_GRID>{P, d, d + n, d + 5 * n});
+        else be.launch(n, EvalRhsPhase<FIELD_PROGRAM>{P, d, d + n, d + 5 * n});
+        be.download(dy, d + 5 * n, sizeof(double) * 4 * n);
+        return check();
+    }
+    int eval_flow(int64_t n, const double* t, const double* x, double* w, double* jac) {
+        if (P.field.kind < 0) return fail(DABRY_ERR_INVALID, "no flow field set");
+        double* d = (double*) scratch(sizeof(double) * n * 9);
+        if (!d) return fail(DABRY_ERR_CAPACITY, "out of device memory");
+        be.upload(d, t, sizeof(double) * n);
+        be.upload(d + n, x, sizeof(double) * 2 * n);
+        if (P.field.kind == FIELD_GRID) be.launch(n, EvalFlowPhase<FIELD_GRID>{P, d, d + n, d + 3 * n, d + 5 * n});
+        else be.launch(n, EvalFlowPhase<FIELD_PROGRAM>{P, d, d + n, d + 3 * n, d + 5 * n});
+        be.download(w, d + 3 * n, sizeof(double) * 2 * n);
+        be.download(jac, d + 5 * n, sizeof(double) * 4 * n);
+        return check();
+    }
+
+    int fail(int code, const std::string& msg) {
+        err = msg;
+        return code;
+    }
+
+private:
+    std::vector<double> times_h;
+    double* d_times = nullptr;
+    double* d_tables = nullptr;
+    double* d_grid = nullptr;
+    int32_t* d_request = nullptr;
+    int32_t* d_offset = nullptr;
+    int32_t* d_list = nullptr;
+    double* d_map = nullptr;
+    int32_t* d_arr_index = nullptr;
+    double* d_arr_cost = nullptr;
+    Counters* d_counters = nullptr;
+    void* d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+    int64_t aux_capacity = 0;
+    int64_t n_sites = 0;
+    int32_t shoot_begin = 0, shoot_end = 0;
+    int variant = DABRY_RESAMPLING;
+    int has_ghost = 0;
+    int round = 0, i_subframe = 0;
+    int64_t last_new = 0;
+    int64_t solution_site = -1;
+    double solution_cost = NAN;
+    bool arrivals_ready = false;
+
+    void set_wrapper(const dabry_wrapper* w) {
+        FieldDesc& F = P.field;
+        F.time_origin = w ? w->time_origin : 0.;
+        F.scale_time = w ? w->scale_time : 1.;
+        F.scale_length = w ? w->scale_length : 1.;
+        F.wbl[0] = w ? w->bl[0] : 0.;
+        F.wbl[1] = w ? w->bl[1] : 0.;
+        F.scaler_speed = w ? w->scaler_speed : 1.;
+        F.scaler_dspeed = w ? w->scaler_dspeed : 1.;
+    }
+
+    int check() {
+        if (!be.ok()) return fail(DABRY_ERR_CUDA, be.error());
+        return DABRY_OK;
+    }
+
+    void* scratch(size_t bytes) {
+        if (bytes > scratch_bytes) {
+            be.free(d_scratch);
+            d_scratch = be.alloc(bytes);
+            scratch_bytes = d_scratch ? bytes : 0;
+        }
+        return d_scratch;
+    }
+
+    int ensure_aux(int64_t n) {
+        if (n <= aux_capacity) return DABRY_OK;
+        const int64_t cap = n + n / 2 + 1024;
+        be.free(d_request);
+        be.free(d_offset);
+        be.free(d_list);
+        be.free(d_arr_index);
+        be.free(d_arr_cost);
+        d_request = (int32_t*) be.alloc(sizeof(int32_t) * cap);
+        d_offset = (int32_t*) be.alloc(sizeof(int32_t) * cap);
+        d_list = (int32_t*) be.alloc(sizeof(int32_t) * cap);
+        d_arr_index = (int32_t*) be.alloc(sizeof(int32_t) * cap);
+        d_arr_cost = (double*) be.alloc(sizeof(double) * cap);
+        if (!d_request || !d_offset || !d_list || !d_arr_index || !d_arr_cost)
+            return fail(DABRY_ERR_CAPACITY, "out of device memory (aux)");
+        aux_capacity = cap;
+        arrivals_ready = false;
+        return DABRY_OK;
+    }
+
+    template <class T>
+    bool grow(T*& p, int64_t old_cap, int64_t new_cap, int64_t rows, int64_t per) {
+        // [rows][cap * per] arrays: re-pitch row by row
+        T* q = (T*) be.alloc(sizeof(T) * rows * new_cap * per);
+        if (!q) return false;
+        if (p && n_sites > 0)
+            be.copy2d(q, sizeof(T) * new_cap * per, p, sizeof(T) * old_cap * per, sizeof(T) * n_sites * per, rows);
+        be.free(p);
+        p = q;
+        return true;
+    }
+
+    void free_store(SiteStore& s) {
+        be.free(s.xp); be.free(s.ctrl); be.free(s.tt); be.free(s.cost0); be.free(s.t_enter_obs);
+        be.free(s.index_t_init); be.free(s.n_samples); be.free(s.closure); be.free(s.neuter);
+        be.free(s.index_neutered); be.free(s.obstacle); be.free(s.index_t_obs); be.free(s.trigo);
+        be.free(s.check_next); be.free(s.depth); be.free(s.flags); be.free(s.parent_prev); be.free(s.parent_next);
+        be.free(s.created_subframe); be.free(s.valid_first); be.free(s.valid_last); be.free(s.dyadic);
+        be.free(s.next_nb); be.free(s.n_target_events); be.free(s.t_target_events); be.free(s.ivp_status);
+    }
+
+    int reserve(int64_t want) {
+        if (want <= S.capacity) return DABRY_OK;
+        if (want > INT_MAX / 2) return fail(DABRY_ERR_CAPACITY, "more than 2^30 sites");
+        int64_t cap = S.capacity > 0 ? S.capacity + S.capacity / 2 : want;
+        if (cap < want) cap = want;
+        cap = (cap + 31) / 32 * 32;  // keep rows 256-byte aligned
+        const int64_t oc = S.capacity, T = cfg.n_time;
+        bool ok = true;
+        // controls and neighbour links start as NaN / -1 everywhere (free arcs never write controls)
+        Control* nctrl = (Control*) be.alloc(sizeof(Control) * T * cap);
+        int32_t* nnb = (int32_t*) be.alloc(sizeof(int32_t) * T * cap);
+        if (!nctrl || !nnb) return fail(DABRY_ERR_CAPACITY, "out of device memory (site store)");
+        be.launch(2 * T * cap, FillF64Phase{(double*) nctrl, quiet_nan()});
+        be.launch(T * cap, FillI32Phase{nnb, -1});
+        if (S.ctrl && n_sites > 0) {
+            be.copy2d(nctrl, sizeof(Control) * cap, S.ctrl, sizeof(Control) * oc, sizeof(Control) * n_sites, T);
+            be.copy2d(nnb, sizeof(int32_t) * cap, S.next_nb, sizeof(int32_t) * oc, sizeof(int32_t) * n_sites, T);
+        }
+        be.free(S.ctrl);
+        be.free(S.next_nb);
+        S.ctrl = nctrl;
+        S.next_nb = nnb;
+        ok = ok && grow(S.xp, oc, cap, T, 1) && grow(S.tt, oc, cap, T, 1);
+        ok = ok && grow(S.cost0, oc, cap, 1, 1) && grow(S.t_enter_obs, oc, cap, 1, 1);
+        ok = ok && grow(S.index_t_init, oc, cap, 1, 1) && grow(S.n_samples, oc, cap, 1, 1);
+        ok = ok && grow(S.closure, oc, cap, 1, 1) && grow(S.neuter, oc, cap, 1, 1);
+        ok = ok && grow(S.index_neutered, oc, cap, 1, 1) && grow(S.obstacle, oc, cap, 1, 1);
+        ok = ok && grow(S.index_t_obs, oc, cap, 1, 1) && grow(S.trigo, oc, cap, 1, 1);
+        ok = ok && grow(S.check_next, oc, cap, 1, 1) && grow(S.depth, oc, cap, 1, 1);
+        ok = ok && grow(S.flags, oc, cap, 1, 1) && grow(S.parent_prev, oc, cap, 1, 1);
+        ok = ok && grow(S.parent_next, oc, cap, 1, 1) && grow(S.created_subframe, oc, cap, 1, 1);
+        ok = ok && grow(S.valid_first, oc, cap, 1, 1) && grow(S.valid_last, oc, cap, 1, 1);
+        ok = ok && grow(S.dyadic, oc, cap, 1, 1) && grow(S.n_target_events, oc, cap, 1, 1);
+        ok = ok && grow(S.t_target_events, oc, cap, 1, DABRY_MAX_TARGET_EVENTS) && grow(S.ivp_status, oc, cap, 1, 1);
+        if (!ok) return fail(DABRY_ERR_CAPACITY, "out of device memory (site store)");
+        S.capacity = (int32_t) cap;
+        S.n_time = cfg.n_time;
+        S.t_init = cfg.t_init;
+        S.times = d_times;
+        be.sync();
+        return check();
+    }
+
+    int integrate(const int32_t* list, int32_t base, int64_t n, int index_t) {
+        be.tic();
+        if (P.field.kind == FIELD_GRID) {
+            IntegratePhase<FIELD_GRID> ph{P, C, S, list, base, index_t, d_counters};
+            be.launch(n, ph);
+        } else {
+            IntegratePhase<FIELD_PROGRAM> ph{P, C, S, list, base, index_t, d_counters};
+            be.launch(n, ph);
+        }
+        ConnectPhase cp{S, list, base};
+        be.launch(n, cp);
+        stats.ms_integrate += be.toc();
+        return check();
+    }
+
+    // compute_new_sites(index_t_hi) (solver_ef.py:630-665); new sites become [shoot_begin, shoot_end)
+    int resample(int index_t_hi, int subframe) {
+        if (int rc = ensure_aux(n_sites)) return rc;
+        be.tic();
+        ResamplePhase rp{P, C, S, index_t_hi, d_request};
+        be.launch(n_sites, rp);
+        const int64_t n_new = be.scan_requests(d_request, n_sites, d_offset, nullptr);
+        if (n_new > 0) {
+            if (int rc = reserve(n_sites + n_new)) return rc;
+            SpawnPhase sp{C, S, d_request, d_offset, (int32_t) n_sites, subframe};
+            be.launch(n_sites, sp);
+        }
+        shoot_begin = (int32_t) n_sites;
+        n_sites += n_new;
+        shoot_end = (int32_t) n_sites;
+        last_new = n_new;
+        arrivals_ready = false;
+        stats.ms_resample += be.toc();
+        return check();
+    }
+
+    int build_cost_map(int k_lo, int k_hi, int all_sites, int subframe, int va, int vb) {
+        be.launch((int64_t) C.cm_nx * C.cm_ny, FillF64Phase{d_map, INFINITY});
+        const int lo = imax(k_lo, 0);
+        if (k_hi >= lo && n_sites > 0) {
+            RasterPhase rp{C, S, d_map, (int32_t) n_sites, lo, k_hi, subframe, va, vb, all_sites};
+            be.launch(n_sites * (int64_t) (k_hi - lo + 1), rp);
+        }
+        return check();
+    }
+
+    // SolverEFTrimming.trim (solver_ef.py:819-841)
+    int trim(int target) {
+        be.tic();
+        const int q = cfg.n_index_per_subframe;
+        const int start_cm = i_subframe + 1 - cfg.trimming_band_width;
+        // self.sites_valid[start_cm : i_subframe + 1] with Python slice semantics on a list of n_subframes + 1 sets:
+        // a negative start counts from the END of the list, which leaves the slice empty for the first sub-frames
+        const int len = n_subframes() + 1;
+        int a = start_cm < 0 ? imax(start_cm + len, 0) : imin(start_cm, len);
+        int b = imin(i_subframe + 1, len);
+        if (int rc = build_cost_map(start_cm * q, target, 0, i_subframe, a, b)) return rc;
+        TrimPhase tp{C, S, d_map, i_subframe, target};
+        be.launch(n_sites, tp);
+        stats.ms_trim += be.toc();
+        return check();
+    }
+};
+
+}  // namespace dabry

@@ -1,0 +1,336 @@
+// Flow field evaluation: value w(t, x) and Jacobian J[a][b] = d w_a / d x_b in ONE pass.
+//
+// Two families (reference: dabry/flowfield.py):
+//  * FIELD_GRID    - DiscreteFF (flowfield.py:178-515): N-linear clipped interpolation of the node values AND of
+//                    the node gradients on the same 8 (4 if steady) nodes (misc.py:570-589, flowfield.py:451-472);
+//  * FIELD_PROGRAM - a flattened expression tree of analytic leaves (flowfield.py:66-92 composition,
+//                    565-1134 leaves): value = sum_i coeff_i * leaf_i.
+// Both are seen through the non-dimensionalising WrapperFF (flowfield.py:518-544); identity parameters
+// (time_origin 0, scales 1, bl 0) reproduce an unwrapped field bit for bit.
+//
+// HBM layout of a grid ("pair records"): for every (k, i, j) one 96-byte record
+//     { (c_k, c_k+1) : c in u, v, du/dx, du/dy, dv/dx, dv/dy }        frame k+1 clipped to nt-1
+// i.e. the two frames a time lerp needs are interleaved, a node is six aligned 16-byte loads, and the two
+// nodes (j, j+1) of a cell edge are one contiguous 192-byte run (y is the fastest grid axis, as in the
+// reference's values[k, i, j, :]).
+#pragma once
+#include "common.cuh"
+
+namespace dabry {
+
+enum FieldKind : int32_t { FIELD_PROGRAM = 0, FIELD_GRID = 1 };
+
+enum LeafKind : int32_t {
+    LEAF_UNIFORM = 0,       // p: value(2)                                    flowfield.py:601-620
+    LEAF_STATE_LINEAR = 1,  // p: gradient(4 row-major), origin(2), value_origin(2)   :730-752, :783-804
+    LEAF_GYRE = 2,          // p: center(2), kx, ky, ampl                     :807-833
+    LEAF_VORTEX = 3,        // p: center(2), circulation                      :623-649
+    LEAF_RANKINE = 4,       // p: center(2), circulation, radius | table rows (cx, cy, gamma, radius)  :652-727
+    LEAF_CHERTOVSKIH = 5,   //                                                :1089-1099
+    LEAF_TRAP = 6,          // p[0]: rel_wid; table rows (ff_val, cx, cy, radius)   :1035-1086
+    LEAF_RADIAL_GAUSS = 7,  // p: center(2), radius, sdev, v_max              :860-903
+};
+
+struct FieldLeaf {
+    int32_t kind;
+    int32_t nt;         // > 0: parameters are a time table of nt rows x 4 doubles (FlowField._index, :152-175)
+    int32_t table_off;  // offset (in doubles) of the table inside FieldDesc::tables
+    int32_t pad_;
+    double coeff;       // signed product of the scalings on the path from the tree root
+    double t_start, t_end;
+    double p[8];
+};
+
+struct GridDesc {
+    const double* data;  // pair records, 12 doubles per (k, i, j)
+    int32_t nt, nx, ny;
+    int32_t unsteady;    // 0: 2-D interpolation (flowfield.py:451-452, 466-468); nt == 1
+    double lo[3];        // bounds[:, 0] for (t, x, y); lo[0] unused when steady
+    double spacing[3];   // (hi - lo) / (n - 1), flowfield.py:198-199
+};
+
+struct FieldDesc {
+    int32_t kind;
+    int32_t n_leaves;
+    const double* tables;
+    GridDesc grid;
+    // WrapperFF (flowfield.py:522-544)
+    double time_origin, scale_time, scale_length, wbl[2], scaler_speed, scaler_dspeed;
+    FieldLeaf leaves[DABRY_MAX_LEAVES];
+};
+
+struct Flow {  // w and J at one point
+    double w0, w1, j00, j01, j10, j11;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// FlowField._index (flowfield.py:152-175): lower frame and lerp coefficient of a time-tabulated parameter set
+DABRY_HD void time_index(const FieldLeaf& L, double t, int& i, double& alpha) {
+    const int nt = L.nt;
+    i = 0;
+    alpha = 0.;
+    if (nt <= 1) return;
+    const double t_min = dmin(L.t_start, L.t_end), t_max = dmax(L.t_start, L.t_end);
+    if (t <= t_min) return;
+    if (t > t_max) {
+        i = nt - 2;
+        alpha = 1.;
+        return;
+    }
+    const double tau = (t - t_min) / (t_max - t_min);
+    const double s = tau * (nt - 1);
+    i = (int) s;
+    alpha = s - (double) i;
+    if (i == nt - 1) {
+        i = nt - 2;
+        alpha = 1.;
+    }
+}
+
+DABRY_HD void leaf_eval(const FieldLeaf& L, const double* __restrict__ tables, double t, double x0, double x1,
+                        Flow& o) {
+    o.w0 = o.w1 = o.j00 = o.j01 = o.j10 = o.j11 = 0.;
+    switch (L.kind) {
+    case LEAF_UNIFORM:
+        o.w0 = L.p[0];
+        o.w1 = L.p[1];
+        break;
+    case LEAF_STATE_LINEAR: {
+        const double d0 = x0 - L.p[4], d1 = x1 - L.p[5];
+        o.w0 = (L.p[0] * d0 + L.p[1] * d1) + L.p[6];
+        o.w1 = (L.p[2] * d0 + L.p[3] * d1) + L.p[7];
+        o.j00 = L.p[0];
+        o.j01 = L.p[1];
+        o.j10 = L.p[2];
+        o.j11 = L.p[3];
+        break;
+    }
+    case LEAF_GYRE: {
+        const double kx = L.p[2], ky = L.p[3], ampl = L.p[4];
+        const double a = kx * (x0 - L.p[0]), b = ky * (x1 - L.p[1]);
+        double sa, ca, sb, cb;
+        sincos(a, &sa, &ca);
+        sincos(b, &sb, &cb);
+        o.w0 = ampl * (-sa * cb);
+        o.w1 = ampl * (ca * sb);
+        o.j00 = ampl * (-kx * ca * cb);
+        o.j01 = ampl * (ky * sa * sb);
+        o.j10 = ampl * (-kx * sa * sb);
+        o.j11 = ampl * (ky * ca * cb);
+        break;
+    }
+    case LEAF_VORTEX: {
+        const double dx = x0 - L.p[0], dy = x1 - L.p[1];
+        const double r = sqrt(dx * dx + dy * dy);
+        const double c = L.p[2] / (2 * M_PI * r);
+        o.w0 = c * (-dy / r);
+        o.w1 = c * (dx / r);
+        const double r2 = r * r;
+        const double g = L.p[2] / (2 * M_PI * (r2 * r2));
+        o.j00 = g * (2 * dx * dy);
+        o.j01 = g * (dy * dy - dx * dx);
+        o.j10 = o.j01;
+        o.j11 = g * (-2 * dx * dy);
+        break;
+    }
+    case LEAF_RANKINE: {
+        double cx, cy, gamma, radius;
+        if (L.nt > 0) {
+            int i;
+            double al;
+            time_index(L, t, i, al);
+            const double* r0 = tables + L.table_off + 4 * i;
+            const double* r1 = r0 + 4;
+            cx = (1 - al) * r0[0] + al * r1[0];
+            cy = (1 - al) * r0[1] + al * r1[1];
+            gamma = (1 - al) * r0[2] + al * r1[2];
+            radius = (1 - al) * r0[3] + al * r1[3];
+        } else {
+            cx = L.p[0];
+            cy = L.p[1];
+            gamma = L.p[2];
+            radius = L.p[3];
+        }
+        const double a = x0 - cx, b = x1 - cy;
+        const double r = sqrt(a * a + b * b);
+        if (r < 1e-3 * radius) break;  // zero_ceil (flowfield.py:677, 695, 708)
+        const double et0 = -b / r, et1 = a / r;
+        const double f = gamma / (2 * M_PI);
+        if (r <= radius) {
+            const double s = f * r / (radius * radius);
+            o.w0 = s * et0;
+            o.w1 = s * et1;
+            const double r3 = r * r * r;
+            const double g = f / (radius * radius);
+            // columns: a / r * e_theta + r * d e_theta/dx ,  b / r * e_theta + r * d e_theta/dy
+            o.j00 = g * (a / r * et0 + r * (a * b / r3));
+            o.j10 = g * (a / r * et1 + r * (b * b / r3));
+            o.j01 = g * (b / r * et0 + r * (-(a * a) / r3));
+            o.j11 = g * (b / r * et1 + r * (-(a * b) / r3));
+        } else {
+            const double s = f * 1. / r;
+            o.w0 = s * et0;
+            o.w1 = s * et1;
+            const double r2 = r * r;
+            const double g = f / (r2 * r2);
+            o.j00 = g * (2 * a * b);
+            o.j01 = g * (b * b - a * a);
+            o.j10 = o.j01;
+            o.j11 = g * (-2 * a * b);
+        }
+        break;
+    }
+    case LEAF_CHERTOVSKIH:
+        o.w0 = x0 * (x1 + 3) / 4;
+        o.w1 = -x0 * x0;
+        o.j00 = (x1 + 3) / 4;
+        o.j01 = x0 / 4;
+        o.j10 = -2 * x0;
+        o.j11 = 0.;
+        break;
+    case LEAF_TRAP: {
+        int i;
+        double al;
+        time_index(L, t, i, al);
+        const double* r0 = tables + L.table_off + 4 * i;
+        const double* r1 = r0 + 4;
+        const bool lo_only = al < 1e-3;  // flowfield.py:1064-1066
+        const double ffv = (1 - al) * r0[0] + (lo_only ? 0. : al * r1[0]);
+        const double cx = (1 - al) * r0[1] + (lo_only ? 0. : al * r1[1]);
+        const double cy = (1 - al) * r0[2] + (lo_only ? 0. : al * r1[2]);
+        const double radius = (1 - al) * r0[3] + (lo_only ? 0. : al * r1[3]);
+        const double a = x0 - cx, b = x1 - cy;
+        const double d2 = a * a + b * b;
+        if (d2 < 1e-8 * (radius * radius)) break;
+        const double r = sqrt(d2);
+        const double e0 = a / r, e1 = b / r;
+        const double wid = radius * L.p[0];
+        const double s = 1. / (1. + exp(-4. / wid * (r - radius)));
+        const double ds = (4. / wid) * s * (1. - s);
+        o.w0 = -ffv * s * e0;
+        o.w1 = -ffv * s * e1;
+        // P = ((e0, e1), (-e1 / r, e0 / r));  J = -ff_val * P^T diag(ds, s) P
+        const double q0 = -e1 / r, q1 = e0 / r;
+        o.j00 = -ffv * (e0 * ds * e0 + q0 * s * q0);
+        o.j01 = -ffv * (e0 * ds * e1 + q0 * s * q1);
+        o.j10 = -ffv * (e1 * ds * e0 + q1 * s * q0);
+        o.j11 = -ffv * (e1 * ds * e1 + q1 * s * q1);
+        break;
+    }
+    case LEAF_RADIAL_GAUSS: {
+        const double a = x0 - L.p[0], b = x1 - L.p[1];
+        const double radius = L.p[2], sdev = L.p[3], vmax = L.p[4];
+        const double r = sqrt(a * a + b * b);
+        if (r < 1e-3 * radius) break;
+        const double e0 = a / r, e1 = b / r;
+        const double lg = log(r / radius);
+        const double amp = vmax * exp(-(lg * lg) / (2 * sdev * sdev));
+        o.w0 = amp * e0;
+        o.w1 = amp * e1;
+        const double c = -lg * amp / (r * r * sdev * sdev);
+        const double dv0 = c * a, dv1 = c * b;
+        const double r3 = r * r * r;
+        o.j00 = e0 * dv0 + amp * (b * b / r3);
+        o.j01 = e0 * dv1 + amp * (-a * b / r3);
+        o.j10 = e1 * dv0 + amp * (-a * b / r3);
+        o.j11 = e1 * dv1 + amp * (a * a / r3);
+        break;
+    }
+    default:
+        break;
+    }
+}
+
+// Node loads: on the device the six 16-byte halves of a pair record go through the read-only path.
+struct D2 {
+    double x, y;
+};
+DABRY_HD D2 load_pair(const double* p) {
+#if defined(__CUDA_ARCH__)
+    const double2 v = __ldg(reinterpret_cast<const double2*>(p));
+    return D2{v.x, v.y};
+#else
+    return D2{p[0], p[1]};
+#endif
+}
+
+// Utils.interpolate (misc.py:570-589) on values and grad_values at once.  Weights come from the UNCLIPPED
+// floor; indices lo and lo + 1 are clipped independently to [0, n - 1]; no wrap in longitude.
+DABRY_HD void grid_eval(const GridDesc& G, double t, double x0, double x1, Flow& o) {
+    double wt_lo = 1., wt_hi = 0.;
+    int kp = 0;
+    bool t_same = false;
+    if (G.unsteady) {
+        const double pos = (t - G.lo[0]) / G.spacing[0];
+        const double fl = floor(pos);
+        wt_hi = pos - fl;
+        wt_lo = 1. - wt_hi;
+        const int k = (int) fl;
+        kp = iclamp(k, 0, G.nt - 1);
+        t_same = k < 0;  // both clipped indices are frame 0
+    }
+    const double px = (x0 - G.lo[1]) / G.spacing[1];
+    const double py = (x1 - G.lo[2]) / G.spacing[2];
+    const double fx = floor(px), fy = floor(py);
+    const double wx_hi = px - fx, wy_hi = py - fy;
+    const double wx_lo = 1. - wx_hi, wy_lo = 1. - wy_hi;
+    const int i0 = iclamp((int) fx, 0, G.nx - 1), i1 = iclamp((int) fx + 1, 0, G.nx - 1);
+    const int j0 = iclamp((int) fy, 0, G.ny - 1), j1 = iclamp((int) fy + 1, 0, G.ny - 1);
+    const int64_t plane = (int64_t) kp * G.nx;
+    const double* n00 = G.data + ((plane + i0) * G.ny + j0) * 12;
+    const double* n01 = G.data + ((plane + i0) * G.ny + j1) * 12;
+    const double* n10 = G.data + ((plane + i1) * G.ny + j0) * 12;
+    const double* n11 = G.data + ((plane + i1) * G.ny + j1) * 12;
+    const double w00 = wx_lo * wy_lo, w01 = wx_lo * wy_hi, w10 = wx_hi * wy_lo, w11 = wx_hi * wy_hi;
+    double acc[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        const D2 a = load_pair(n00 + 2 * c), b = load_pair(n01 + 2 * c);
+        const D2 d = load_pair(n10 + 2 * c), e = load_pair(n11 + 2 * c);
+        const double ta = wt_lo * a.x + wt_hi * (t_same ? a.x : a.y);
+        const double tb = wt_lo * b.x + wt_hi * (t_same ? b.x : b.y);
+        const double td = wt_lo * d.x + wt_hi * (t_same ? d.x : d.y);
+        const double te = wt_lo * e.x + wt_hi * (t_same ? e.x : e.y);
+        acc[c] = ((w00 * ta + w01 * tb) + w10 * td) + w11 * te;
+    }
+    o.w0 = acc[0];
+    o.w1 = acc[1];
+    o.j00 = acc[2];
+    o.j01 = acc[3];
+    o.j10 = acc[4];
+    o.j11 = acc[5];
+}
+
+// WrapperFF.value / d_value (flowfield.py:538-544) around either family.
+template <int FK>
+DABRY_HD void field_eval(const FieldDesc& F, double t, double x0, double x1, Flow& o) {
+    const double tt = F.time_origin + t * F.scale_time;
+    const double xx0 = F.wbl[0] + x0 * F.scale_length;
+    const double xx1 = F.wbl[1] + x1 * F.scale_length;
+    if (FK == FIELD_GRID) {
+        grid_eval(F.grid, tt, xx0, xx1, o);
+    } else {
+        Flow acc = {0., 0., 0., 0., 0., 0.};
+        for (int l = 0; l < F.n_leaves; ++l) {
+            Flow f;
+            leaf_eval(F.leaves[l], F.tables, tt, xx0, xx1, f);
+            const double c = F.leaves[l].coeff;
+            if (l == 0) {
+                acc.w0 = c * f.w0; acc.w1 = c * f.w1;
+                acc.j00 = c * f.j00; acc.j01 = c * f.j01; acc.j10 = c * f.j10; acc.j11 = c * f.j11;
+            } else {
+                acc.w0 += c * f.w0; acc.w1 += c * f.w1;
+                acc.j00 += c * f.j00; acc.j01 += c * f.j01; acc.j10 += c * f.j10; acc.j11 += c * f.j11;
+            }
+        }
+        o = acc;
+    }
+    o.w0 *= F.scaler_speed;
+    o.w1 *= F.scaler_speed;
+    o.j00 *= F.scaler_dspeed;
+    o.j01 *= F.scaler_dspeed;
+    o.j10 *= F.scaler_dspeed;
+    o.j11 *= F.scaler_dspeed;
+}
+
+}  // namespace dabry

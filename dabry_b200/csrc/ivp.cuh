@@ -1,0 +1,155 @@
+// scipy.integrate.solve_ivp's driver loop restated for one extremal per thread (scipy 1.18.1,
+// scipy/integrate/_ivp/ivp.py:659-732): step, event detection (find_active_events :134-158, all events of the
+// reference have direction -1, misc.py:34-43), roots by brentq on the dense output (solve_event_equation
+// :52-77), earliest terminal root truncates the step (handle_events :80-131), t_eval sampling through the
+// dense output with searchsorted(side='right') (:711-728).
+//
+// The callers are the three solve_ivp call sites of the reference: solver_ef.py:427-429 / 494-496 (free arc,
+// N = 4), :528-532 (one-sample constrained arc, N = 2, no event), :557-561 (constrained arc with quit event).
+#pragma once
+#include "rk45.cuh"
+
+namespace dabry {
+
+#define DABRY_MAX_EVENTS (1 + DABRY_MAX_OBSTACLES)
+
+enum IvpStatus : int32_t { IVP_FINISHED = 0, IVP_TERMINATED = 1, IVP_FAILED = -1 };
+
+// t_eval = numpy.linspace(t_start, t_end, n)[first:] (solver_ef.py:488, 495): j * step + t_start with the last
+// element overwritten by t_end (numpy/_core/function_base.py linspace); products and sums individually rounded.
+struct EvalGrid {
+    double t_start, t_end, step;
+    int n, first;
+    DABRY_HD double at(int j) const {  // j indexes the un-sliced linspace
+        return j == n - 1 ? t_end : add_rn(mul_rn((double) j, step), t_start);
+    }
+};
+
+DABRY_HD EvalGrid make_eval_grid(double t_start, double t_end, int n, int first) {
+    EvalGrid g;
+    g.t_start = t_start;
+    g.t_end = t_end;
+    g.n = n;
+    g.first = first;
+    g.step = n > 1 ? (t_end - t_start) / (double) (n - 1) : 0.;
+    return g;
+}
+
+template <int N>
+struct IvpResult {
+    int32_t status;
+    int32_t n_emitted;       // number of t_eval samples produced
+    int32_t term_event;      // index of the terminal event that stopped the integration, -1 if none
+    double t_term;           // its root
+    double y_term[N];        // sol(t_term)
+};
+
+// Events concept:  int count() const;  bool terminal(int e) const;  double value(int e, double t, const double* y) const;
+//                  void record(int e, double t_root);
+// Sink concept:    void emit(int j, double t, const double* y);     j indexes the un-sliced linspace
+template <int N, class Rhs, class Events, class Sink>
+DABRY_HD void solve_ivp(const Rhs& rhs, Events& events, Sink& sink, double t0, double tf, const double* y0,
+                        const EvalGrid& grid, double max_step, double rtol, double atol, IvpResult<N>& res,
+                        unsigned& n_attempts) {
+    RkState<N> S;
+    rk_init<N>(S, rhs, t0, y0, tf, max_step, rtol, atol);
+    const int ne = events.count();
+    double g[DABRY_MAX_EVENTS];
+    for (int e = 0; e < ne; ++e) g[e] = events.value(e, t0, y0);
+    int eval_i = grid.first;
+    res.status = IVP_FINISHED;
+    res.n_emitted = 0;
+    res.term_event = -1;
+    res.t_term = 0.;
+    bool finished = false;
+    while (!finished) {
+        // OdeSolver.step (base.py): a solver already at t_bound finishes without stepping
+        if (S.t == tf) {
+            S.t_old = S.t;
+            finished = true;
+        } else {
+            if (!rk_step<N>(S, rhs, tf, max_step, rtol, atol, n_attempts)) {
+                res.status = IVP_FAILED;
+                return;
+            }
+            if (S.t - tf >= 0.) finished = true;
+        }
+        const double t_old = S.t_old;
+        double t = S.t;
+        Dense<N> D;
+        bool have_dense = false;
+        bool terminate = false;
+        if (ne > 0) {
+            double g_new[DABRY_MAX_EVENTS];
+            int act[DABRY_MAX_EVENTS];
+            int na = 0;
+            for (int e = 0; e < ne; ++e) {
+                g_new[e] = events.value(e, t, S.y);
+                if (g[e] >= 0. && g_new[e] <= 0.) act[na++] = e;
+            }
+            if (na > 0) {
+                rk_dense<N>(S, D);
+                have_dense = true;
+                double roots[DABRY_MAX_EVENTS];
+                bool any_terminal = false;
+                for (int a = 0; a < na; ++a) {
+                    const int e = act[a];
+                    roots[a] = brentq([&](double tt) {
+                        double yy[N];
+                        dense_eval<N>(D, tt, yy);
+                        return events.value(e, tt, yy);
+                    }, t_old, t);
+                    any_terminal = any_terminal || events.terminal(e);
+                }
+                int keep = na;
+                if (any_terminal) {
+                    // argsort(roots) on a tiny array (insertion sort, stable), cut after the first terminal
+                    for (int a = 1; a < na; ++a) {
+                        const double r = roots[a];
+                        const int e = act[a];
+                        int b = a - 1;
+                        while (b >= 0 && roots[b] > r) {
+                            roots[b + 1] = roots[b];
+                            act[b + 1] = act[b];
+                            --b;
+                        }
+                        roots[b + 1] = r;
+                        act[b + 1] = e;
+                    }
+                    for (int a = 0; a < na; ++a)
+                        if (events.terminal(act[a])) {
+                            keep = a + 1;
+                            break;
+                        }
+                    terminate = true;
+                }
+                for (int a = 0; a < keep; ++a) events.record(act[a], roots[a]);
+                if (terminate) {
+                    res.status = IVP_TERMINATED;
+                    res.term_event = act[keep - 1];
+                    t = roots[keep - 1];
+                    res.t_term = t;
+                    dense_eval<N>(D, t, res.y_term);
+                    finished = true;
+                }
+            }
+            for (int e = 0; e < ne; ++e) g[e] = g_new[e];
+        }
+        // t_eval values <= t that were not emitted yet
+        while (eval_i < grid.n) {
+            const double te = grid.at(eval_i);
+            if (!(te <= t)) break;
+            if (!have_dense) {
+                rk_dense<N>(S, D);
+                have_dense = true;
+            }
+            double yy[N];
+            dense_eval<N>(D, te, yy);
+            sink.emit(eval_i, te, yy);
+            ++eval_i;
+            ++res.n_emitted;
+        }
+    }
+}
+
+}  // namespace dabry

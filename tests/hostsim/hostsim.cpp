@@ -1,0 +1,80 @@
+// TEST INFRASTRUCTURE - not part of the dabry_b200 package and never loaded by it.
+//
+// libdabry_hostsim.so = the device headers of dabry_b200/csrc compiled by g++ with a serial backend behind the
+// same C ABI, so that the CPU-only test tier (`pytest -m "not gpu"`, no GPU in the build container) can step
+// through the very source the CUDA kernels are built from and check it against the reference's golden vectors
+// before any GPU time is spent.  It shares the product's source on purpose, so it is NOT the parity oracle (that
+// is oracle/ + tests/golden) and it is not a fallback: dabry_b200/_native.py only ever loads libdabry_b200.so.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <chrono>
+#include <string>
+
+#include "../../dabry_b200/csrc/engine.cuh"
+
+namespace dabry {
+
+class SerialBackend {
+public:
+    static const char* name() { return "hostsim-serial"; }
+    bool open(int) { return true; }
+    bool ok() const { return true; }
+    const std::string& error() const { return err_; }
+    uint64_t launches() const { return launches_; }
+    void* alloc(size_t bytes) { return malloc(bytes ? bytes : 8); }
+    template <class T>
+    void free(T* p) { ::free((void*) p); }
+    void upload(void* d, const void* h, size_t n) { memcpy(d, h, n); }
+    void download(void* h, const void* d, size_t n) { memcpy(h, d, n); }
+    void zero(void* d, size_t n) { memset(d, 0, n); }
+    void copy2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows) {
+        for (size_t r = 0; r < rows; ++r) memcpy((char*) dst + r * dpitch, (const char*) src + r * spitch, width);
+    }
+    void sync() {}
+    template <class F>
+    void launch(int64_t n, const F& f) {
+        ++launches_;
+        for (int64_t i = 0; i < n; ++i) f(i);
+    }
+    int64_t scan_requests(const int32_t* request, int64_t n, int32_t* offset, int32_t* list) {
+        int32_t acc = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            offset[i] = acc;
+            if (request[i] >= 0) {
+                if (list) list[acc] = (int32_t) i;
+                ++acc;
+            }
+        }
+        return acc;
+    }
+    double min_f64(const double* v, int64_t n) {
+        double m = INFINITY;
+        for (int64_t i = 0; i < n; ++i)
+            if (v[i] < m) m = v[i];
+        return m;
+    }
+    int64_t first_equal_f64(const double* v, int64_t n, double value) {
+        for (int64_t i = 0; i < n; ++i)
+            if (v[i] == value) return i;
+        return -1;
+    }
+    void tic() { t0_ = now(); }
+    double toc() { return now() - t0_; }
+    void tic_total() { t1_ = now(); }
+    double toc_total() { return now() - t1_; }
+
+private:
+    static double now() {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    }
+    std::string err_;
+    uint64_t launches_ = 0;
+    double t0_ = 0., t1_ = 0.;
+};
+
+}  // namespace dabry
+
+#define DABRY_BACKEND dabry::SerialBackend
+#include "../../dabry_b200/csrc/capi.inl"
