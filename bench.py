@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""Benchmark of the extremal-field hot path (BASELINE.json: extremal-RK-steps/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload era5|planar|gyre] [--impl reference]
+
+One step = one full `SolverEFResampling` solve (setup, integration of every extremal over the whole horizon with
+events, resampling scan, trim_distance, arrival-time argmin) of the named workload on synthetic data:
+
+  era5   (default) BASELINE config 4: ERA5-shaped spherical grid 1440 x 721 x 24, 1.25 M root extremals PER GPU
+         (10 M over 8 GPUs), max_depth = 1, DOPRI5 restated from scipy, fp64 grid + fp64 state.  Weak scaling.
+  planar BASELINE config 3: planar unsteady DiscreteFF 1024 x 1024 x 48, 2^19 roots per GPU, max_depth = 4.
+  gyre   BASELINE config 2 flow: analytic Gyre, 100 k roots per GPU, max_depth = 1 (fp64 pipe bound, no gather).
+
+`value`  : whole-job RK steps / device time, flow grid resident in HBM, roots generated on the device.
+`e2e`    : the same solve through the public API from HOST arrays: grid upload + repack, root costates upload,
+           solve, arrival arrays and the optimal trajectory read back - all inside the timed region.
+`--impl reference`: the CPU oracle (oracle/solver_port.py: numpy + scipy solve_ivp like the reference) on a bounded
+           sample of the same workload, all host cores (one process per core, independent theta_0 shards).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+BYTES_PER_STEP_DOPRI5_F64 = 2336  # 6 RHS x 8 nodes x 6 scalars x 8 B + 32 B of trajectory output
+WORKLOADS = ('era5', 'planar', 'gyre')
+
+
+def build_problem(workload, small=False):
+    """(problem, total_duration, solver kwargs, description) - identical on every rank."""
+    from dabry_b200 import synthetic
+    from dabry_b200.flowfield import DiscreteFF
+    from dabry_b200.misc import Coords
+    from dabry_b200.problem import NavigationProblem
+    if workload == 'era5':
+        shape = (6, 180, 91) if small else (24, 1440, 721)
+        sc = synthetic.era5_like(*shape)
+        ff = DiscreteFF(sc.values, sc.bounds, Coords.GCS, force_no_diff=True)
+        pb = NavigationProblem(ff, sc.x_init, sc.x_target, sc.srf, bl=sc.bl, tr=sc.tr, name='era5_like').rescale()
+        # fixed horizon: 1.1 x the great-circle time at srf, in the rescaled clock (skips the host heuristics)
+        from dabry_b200.misc import Utils
+        t_gc = Utils.distance(sc.x_init, sc.x_target, Coords.GCS) / sc.srf
+        total = 1.1 * t_gc / (1. / (sc.srf / Utils.EARTH_RADIUS))
+        return pb, total, dict(max_depth=1), 'era5_like %dx%dx%d gcs' % shape
+    if workload == 'planar':
+        shape = (6, 128, 128) if small else (48, 1024, 1024)
+        sc = synthetic.planar_waves(*shape)
+        ff = DiscreteFF(sc.values, sc.bounds, Coords.CARTESIAN, force_no_diff=True)
+        pb = NavigationProblem(ff, sc.x_init, sc.x_target, sc.srf, bl=sc.bl, tr=sc.tr, name='planar_waves').rescale()
+        return pb, sc.total_duration, dict(max_depth=4, max_dist=0.002), 'planar_waves %dx%dx%d' % shape
+    if workload == 'gyre':
+        pb = NavigationProblem.from_name('gyre').rescale()
+        return pb, 1.0, dict(max_depth=1), 'gyre analytic'
+    raise ValueError(workload)
+
+
+def default_roots(workload):
+    return {'era5': 1_250_000, 'planar': 1 << 19, 'gyre': 100_000}[workload]
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+             'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self._stop = threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.QUERY,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5)
+                parts = [p.strip() for p in out.stdout.strip().split(',')]
+                if len(parts) >= 9:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=6)
+        sm = [float(s[1]) for s in self.samples if s[1].replace('.', '').isdigit()]
+        mx = [float(s[2]) for s in self.samples if s[2].replace('.', '').isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), s[5:9]):
+                if v.lower() == 'active':
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(self.samples)}
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(path) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+# ---- CPU oracle legs ---------------------------------------------------------------------------------------
+
+def _oracle_shard(args):
+    workload, small, n_roots, lo, count = args
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import warnings
+    warnings.filterwarnings('ignore')
+    from solver_port import Port
+    pb, total, kw, _ = build_problem(workload, small)
+    inner = getattr(pb.model.ff, 'ff', None)
+    if inner is not None and getattr(inner, 'grad_values', 1) is None:
+        inner.compute_derivatives()  # the GPU arm differentiates on the device; the CPU oracle needs the host copy
+    port = Port(pb, total, n_costate_sectors=n_roots, root_range=(lo, count), max_depth=1)
+    t0 = time.perf_counter()
+    port.run_resampling()
+    return port.n_rk, time.perf_counter() - t0, port.solution_cost
+
+
+def oracle_throughput(workload, small, n_roots, sample_roots, cores):
+    """RK steps/s of the numpy/scipy oracle on `sample_roots` extremals of the workload's fan, split over `cores`
+    processes (independent theta_0 shards).  Returns (steps/s aggregate, steps, seconds)."""
+    from multiprocessing import get_context
+    per = max(1, sample_roots // cores)
+    stride = max(1, n_roots // cores)
+    jobs = [(workload, small, n_roots, min(i * stride, n_roots - per), per) for i in range(cores)]
+    t0 = time.perf_counter()
+    if cores == 1:
+        results = [_oracle_shard(jobs[0])]
+    else:
+        with get_context('spawn').Pool(cores) as pool:
+            results = pool.map(_oracle_shard, jobs)
+    wall = time.perf_counter() - t0
+    steps = sum(r[0] for r in results)
+    busy = max(r[1] for r in results)
+    return steps / busy, steps, busy, wall
+
+
+def run_reference(args, rank, world):
+    """`--impl reference`: the reference's numpy/scipy CPU algorithm (oracle port) on all host cores."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_roots = args.roots_per_gpu * world
+    sample = args.cpu_sample_roots if args.cpu_sample_roots else 2 * cores
+    times = []
+    steps_tot = 0
+    for i in range(args.warmup + args.steps):
+        rate, steps, busy, wall = oracle_throughput(args.workload, args.small, n_roots, sample, cores)
+        if i >= args.warmup:
+            times.append(busy)
+            steps_tot += steps
+    value = steps_tot / sum(times)
+    line = {
+        'impl': 'reference', 'metric': 'extremal_rk_steps_per_sec', 'value': value, 'unit': 'steps/s',
+        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * sum(times) / len(times),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': args.workload + ('-small' if args.small else ''), 'roots_total': n_roots,
+                   'parallelism': 'cpu x%d processes' % cores},
+        'cpu_baseline': {'value': value, 'unit': 'steps/s', 'cores': cores, 'kind': 'port',
+                         'sample': '%d of %d root extremals (theta_0 shards of %d per core), full horizon, per step'
+                                   % (sample, n_roots, max(1, sample // cores))},
+        'e2e': {'value': value, 'unit': 'steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---- GPU arm -----------------------------------------------------------------------------------------------
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--workload', choices=WORKLOADS, default='era5')
+    ap.add_argument('--roots-per-gpu', type=int, default=0)
+    ap.add_argument('--impl', default='b200')
+    ap.add_argument('--small', action='store_true', help='reduced grid (debugging only; not a valid bench number)')
+    ap.add_argument('--cpu-sample-roots', type=int, default=0)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    args = ap.parse_args()
+    if args.roots_per_gpu <= 0:
+        args.roots_per_gpu = default_roots(args.workload)
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        print('note: fewer than 3 warm-up steps requested', file=sys.stderr)
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device: dabry_b200 has no CPU execution path'
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    from dabry_b200 import _native as nat
+    from dabry_b200.distributed import shard_range
+    from dabry_b200.solver_ef import SolverEFResampling
+
+    pb, total, kw, descr = build_problem(args.workload, args.small)
+    n_roots = args.roots_per_gpu * world
+    root_range = shard_range(n_roots, rank, world) if world > 1 else None
+    count = root_range[1] if root_range else n_roots
+    cap_factor = 1.02 if kw.get('max_depth', 1) == 1 else 2.5
+    max_sites = int(count * cap_factor) + 4096
+
+    def make_solver(device_roots):
+        return SolverEFResampling(pb, total, n_costate_sectors=n_roots, root_range=root_range, device=local_rank,
+                                  max_sites=max_sites, device_roots=device_roots, **kw)
+
+    # ---- resident arm: grid uploaded once, K timed solves ----
+    solver = make_solver(device_roots=True)
+    handle = solver._ensure_handle()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')  # > 126 MB L2
+
+    def one_step():
+        flush.zero_()  # L2 flush between iterations
+        torch.cuda.synchronize()
+        handle.call('dabry_solve', nat.RESAMPLING, None)
+        return handle.stats()
+
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    base = handle.stats()
+    dev_ms, integ_ms, steps_rk = [], [], []
+    t_wall = time.perf_counter()
+    for _ in range(args.steps):
+        st = one_step()
+        dev_ms.append(st['ms_total'])
+        integ_ms.append(st['ms_integrate'])
+        steps_rk.append(st['rk_steps'])
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t_wall)
+    clocks = sampler.stop()
+    last = handle.stats()
+    launches = int(last['kernel_launches'] - base['kernel_launches'])
+    n_sites = int(last['n_sites'])
+    cost_resident = handle.solution()[1]
+
+    def reduce_max(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def reduce_sum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    total_dev_ms = reduce_max(float(sum(dev_ms)))
+    total_wall_ms = reduce_max(wall_ms)
+    total_steps = reduce_sum(float(sum(steps_rk)))
+    value = total_steps / (total_dev_ms * 1e-3)
+    integ_total_ms = float(sum(integ_ms))
+    local_steps = float(sum(steps_rk))
+    solver.close()
+    del flush
+
+    # ---- end-to-end arm: public API from host arrays, every step ----
+    e2e = None
+    if not args.no_e2e:
+        ff = pb.model.ff
+        inner = ff.ff
+        h2d = int(inner.values.nbytes + 16 * count)
+
+        def e2e_step():
+            s = make_solver(device_roots=False)
+            s.solve()
+            cost = s.solution_cost
+            d2h = 12 * int(s._arrival_index.shape[0])
+            if s.solution_site is not None:
+                traj = s.solution_site.traj
+                d2h += int(traj.states.nbytes + traj.times.nbytes + traj.costates.nbytes)
+            rk = s.native_stats()['rk_steps']
+            s.close()
+            return cost, rk, d2h
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        rk_sum, d2h = 0, 0
+        n_e2e = max(1, min(args.steps, 3))
+        for _ in range(n_e2e):
+            cost_e2e, rk, d2h = e2e_step()
+            rk_sum += rk
+        barrier()
+        e2e_s = reduce_max(time.perf_counter() - t0)
+        e2e = {'value': reduce_sum(float(rk_sum)) / e2e_s, 'unit': 'steps/s', 'h2d_bytes_per_step': h2d,
+               'd2h_bytes_per_step': int(d2h), 'steps': n_e2e, 'ms_per_step': 1e3 * e2e_s / n_e2e,
+               'arrival_cost': None if np.isnan(cost_e2e) else cost_e2e}
+
+    # ---- CPU baseline (rank 0, N = 1) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = 1
+        sample = args.cpu_sample_roots if args.cpu_sample_roots else 8
+        rate, steps, busy, _ = oracle_throughput(args.workload, args.small, n_roots, sample, cores)
+        cpu = {'value': rate, 'unit': 'steps/s', 'cores': cores, 'kind': 'port',
+               'sample': '%d of %d root extremals, full horizon (%d RK steps in %.1f s); %d host cores present'
+                         % (sample, n_roots, steps, busy, os.cpu_count() or 1)}
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        ach = local_steps * BYTES_PER_STEP_DOPRI5_F64 / (integ_total_ms * 1e-3) / 1e9
+        roofline = {'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
+                    'traffic': None, 'kernel': 'phase_kernel<IntegratePhase>', 'peak_source': peak_src,
+                    'algorithmic_bytes_per_step': BYTES_PER_STEP_DOPRI5_F64,
+                    'kernel_ms_per_launch': integ_total_ms / args.steps,
+                    'note': 'algorithmic bytes (8 nodes x 6 fp64 per RHS, 6 RHS per step, + 32 B output) / measured '
+                            'integrate-kernel time; the touched grid region is L2 resident, see DESIGN.md'}
+        if args.workload == 'gyre':
+            roofline['note'] = 'analytic field: no gather, fp64-pipe bound; fraction of the gather roofline is nominal'
+        line = {
+            'metric': 'extremal_rk_steps_per_sec', 'value': value, 'unit': 'steps/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_dev_ms / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': args.workload + ('-small' if args.small else ''), 'flow': descr,
+                       'roots_per_gpu': args.roots_per_gpu, 'roots_total': n_roots, 'sites_rank0': n_sites,
+                       'integrator': 'dopri5_scipy', 'n_time': 100, 'max_depth': kw.get('max_depth'),
+                       'parallelism': 'theta0-shard x%d' % world, 'l2': 'flushed between steps (256 MiB write)',
+                       'wall_ms_per_step': total_wall_ms / args.steps,
+                       'arrival_cost_rank0': None if np.isnan(cost_resident) else cost_resident},
+            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -2,10 +2,9 @@
 `NavigationProblem.apply_feedback` to bound the time horizon (two scalar ODE solves per problem, host side;
 SURVEY 8f rank 1)."""
 from abc import ABC, abstractmethod
-from math import atan2
-
 import numpy as np
 from numpy import cos, sin
+from numpy import arctan2 as atan2  # numpy's, as in the reference (feedback.py:4): differs from math.atan2 in the last bit
 
 from dabry_b200.misc import Coords, Utils, directional_timeopt_control
 

@@ -164,7 +164,8 @@ class NavigationProblem:
     def apply_feedback(self, fb: Feedback, rel_timeout=10, n_time=1000) -> Trajectory:
         """Integrate the closed loop x' = f(t, x, fb(t, x)) until the target disc is entered (problem.py:193-214)."""
         t0 = self.model.ff.t_start
-        times = np.linspace(t0, t0 + rel_timeout * self.length_reference / self.srf_max, n_time)
+        time_scale = self.length_reference / self.srf_max
+        times = np.linspace(t0, t0 + rel_timeout * time_scale, n_time)
         radius_sq = self.target_radius ** 2
 
         def event_target(t, x):

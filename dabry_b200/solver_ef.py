@@ -431,8 +431,12 @@ class SolverEFResampling(SolverEF):
     apart than `max_dist` (solver_ef.py:447-754)."""
     _VARIANT = nat.RESAMPLING
 
-    def __init__(self, *args, max_dist: Optional[float] = None, mode_origin: bool = True, **kwargs):
+    def __init__(self, *args, max_dist: Optional[float] = None, mode_origin: bool = True,
+                 device_roots: bool = False, **kwargs):
         super().__init__(*args, **kwargs)
+        # device_roots: generate the root costates on the GPU (CUDA sincos, within 1 ulp of numpy's) instead of
+        # uploading numpy's - for very large fans
+        self.device_roots = device_roots
         self.max_dist = max_dist if max_dist is not None else self.target_radius
         self._max_dist_sq = self.max_dist ** 2
         self.mode_origin = mode_origin
@@ -456,6 +460,8 @@ class SolverEFResampling(SolverEF):
     def _root_costates(self):
         """1000 (cos, sin)(theta), theta = linspace(0, 2 pi, n, endpoint=False) (solver_ef.py:465-467): computed
         with numpy so that the device starts from the same bits as the reference."""
+        if self.device_roots:
+            return None
         n = self.n_costate_sectors
         offset, count = (0, n) if self.root_range is None else self.root_range
         theta = np.linspace(0, 2 * np.pi, n, endpoint=False)[offset:offset + count]

@@ -175,3 +175,56 @@ def compare_tolerant(rec, g, tol=FP64_TOL, min_match=0.85):
             same += 1
     assert same >= min_match * len(shared), (same, len(shared))
     return {'shared': len(shared), 'identical': same, 'ours': len(ours), 'theirs': len(theirs)}
+
+
+def port_record(port):
+    """Flatten an oracle `Port` (oracle/solver_port.py) into the golden record layout."""
+    sites = list(port.sites.values())
+    ev = port.event_names
+    n = len(sites)
+    rec = {
+        'n_sites': np.int64(n), 'names': np.array([s.name for s in sites]), 'event_names': np.array(ev),
+        'index_t_init': np.array([s.index_t_init for s in sites], dtype=np.int32),
+        'traj_len': np.array([len(s.t) for s in sites], dtype=np.int32),
+        'closure': np.array([-1 if s.closure is None else s.closure for s in sites], dtype=np.int32),
+        'neuter': np.array([-1 if s.neuter is None else s.neuter for s in sites], dtype=np.int32),
+        'obstacle': np.array([ev.index(s.obstacle_name) if s.obstacle_name else -1 for s in sites], dtype=np.int32),
+        'index_t_obs': np.array([s.index_t_obs for s in sites], dtype=np.int32),
+        'obs_trigo': np.array([bool(s.obs_trigo) for s in sites]),
+        't_enter_obs': np.array([np.nan if s.t_enter_obs is None else s.t_enter_obs for s in sites]),
+        'index_t_check_next': np.array([s.check_next for s in sites], dtype=np.int32),
+        'times': port.times, 'total_duration': np.float64(port.total_duration),
+        'max_int_step': np.float64(port.max_int_step), 'success': np.bool_(port.success),
+        'first': np.array([np.concatenate((s.x[0], s.p[0], s.u[0])) for s in sites]),
+        'last': np.array([np.concatenate((s.x[-1], s.p[-1], s.u[-1])) for s in sites]),
+        'state_sum': np.array([np.sum(np.array(s.x), axis=0) for s in sites]),
+        'solution_name': np.array(port.solution_site.name if port.solution_site is not None else ''),
+        'solution_cost': np.float64(port.solution_cost),
+        'solution_names': np.array(sorted(s.name for s in port.solution_sites)),
+    }
+    offs = np.zeros(n + 1, dtype=np.int64)
+    offs[1:] = np.cumsum(rec['traj_len'])
+    rec['traj_offsets'] = offs
+    rec['traj_times'] = np.concatenate([np.array(s.t) for s in sites])
+    rec['traj_states'] = np.concatenate([np.array(s.x).reshape(-1, 2) for s in sites])
+    rec['traj_costates'] = np.concatenate([np.array(s.p).reshape(-1, 2) for s in sites])
+    rec['traj_controls'] = np.concatenate([np.array(s.u).reshape(-1, 2) for s in sites])
+    rec['traj_cost'] = np.concatenate([np.array(s.cost) for s in sites])
+    return rec
+
+
+def solve_case_port(key, api=None):
+    """Run a registered case through the CPU oracle (oracle/solver_port.py) on `api`'s problem classes
+    (default: this package's)."""
+    from cases import CASES, build_problem, solver_args
+    from solver_port import Port
+    api = package_api() if api is None else api
+    case = CASES[key]
+    pb = build_problem(case, api)
+    args, kwargs = solver_args(case, pb)
+    port = Port(*args, **kwargs)
+    if case.solver == 'T':
+        port.run_trimming()
+    elif case.solver == 'R':
+        port.run_resampling()
+    return case, port
