@@ -76,10 +76,10 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.gpu = gpu_index
         self.samples = []
-        self._stop = threading.Event()
+        self._halt = threading.Event()
 
     def run(self):
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.QUERY,
                                       '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5)
@@ -88,10 +88,10 @@ class ClockSampler(threading.Thread):
                     self.samples.append(parts)
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.2)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=6)
         sm = [float(s[1]) for s in self.samples if s[1].replace('.', '').isdigit()]
         mx = [float(s[2]) for s in self.samples if s[2].replace('.', '').isdigit()]
@@ -253,12 +253,15 @@ def main():
     sampler.start()
     base = handle.stats()
     dev_ms, integ_ms, steps_rk = [], [], []
+    phases = {}
     t_wall = time.perf_counter()
     for _ in range(args.steps):
         st = one_step()
         dev_ms.append(st['ms_total'])
         integ_ms.append(st['ms_integrate'])
         steps_rk.append(st['rk_steps'])
+        for k in ('ms_integrate', 'ms_obstacle', 'ms_resample', 'ms_trim', 'ms_arrival', 'ms_total'):
+            phases[k] = phases.get(k, 0.) + st[k] / args.steps
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t_wall)
     clocks = sampler.stop()
@@ -293,9 +296,8 @@ def main():
     # ---- end-to-end arm: public API from host arrays, every step ----
     e2e = None
     if not args.no_e2e:
-        ff = pb.model.ff
-        inner = ff.ff
-        h2d = int(inner.values.nbytes + 16 * count)
+        inner = getattr(pb.model.ff, 'ff', pb.model.ff)
+        h2d = int((inner.values.nbytes if hasattr(inner, 'values') else 0) + 16 * count)
 
         def e2e_step():
             s = make_solver(device_roots=False)
@@ -327,7 +329,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = 1
-        sample = args.cpu_sample_roots if args.cpu_sample_roots else 8
+        sample = args.cpu_sample_roots if args.cpu_sample_roots else 160
         rate, steps, busy, _ = oracle_throughput(args.workload, args.small, n_roots, sample, cores)
         cpu = {'value': rate, 'unit': 'steps/s', 'cores': cores, 'kind': 'port',
                'sample': '%d of %d root extremals, full horizon (%d RK steps in %.1f s); %d host cores present'
@@ -337,7 +339,7 @@ def main():
         peak, peak_src = measured_peak_gbs()
         ach = local_steps * BYTES_PER_STEP_DOPRI5_F64 / (integ_total_ms * 1e-3) / 1e9
         roofline = {'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
-                    'traffic': None, 'kernel': 'phase_kernel<IntegratePhase>', 'peak_source': peak_src,
+                    'traffic': None, 'kernel': 'phase_kernel<FreeArcPhase<GRID>>', 'peak_source': peak_src,
                     'algorithmic_bytes_per_step': BYTES_PER_STEP_DOPRI5_F64,
                     'kernel_ms_per_launch': integ_total_ms / args.steps,
                     'note': 'algorithmic bytes (8 nodes x 6 fp64 per RHS, 6 RHS per step, + 32 B output) / measured '
@@ -353,6 +355,7 @@ def main():
                        'integrator': 'dopri5_scipy', 'n_time': 100, 'max_depth': kw.get('max_depth'),
                        'parallelism': 'theta0-shard x%d' % world, 'l2': 'flushed between steps (256 MiB write)',
                        'wall_ms_per_step': total_wall_ms / args.steps,
+                       'phase_ms_rank0': {k: round(v, 3) for k, v in phases.items()},
                        'arrival_cost_rank0': None if np.isnan(cost_resident) else cost_resident},
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
         }

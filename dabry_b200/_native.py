@@ -17,7 +17,8 @@ SIMPLE, RESAMPLING, TRIMMING = 0, 1, 2
 CARTESIAN, GCS = 0, 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-DEFAULT_LIBRARY = os.path.join(_HERE, 'libdabry_b200.so')
+# DABRY_B200_LIBRARY: another build of the CUDA library (tuning experiments); there is still no CPU path
+DEFAULT_LIBRARY = os.environ.get('DABRY_B200_LIBRARY', os.path.join(_HERE, 'libdabry_b200.so'))
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
@@ -72,7 +73,7 @@ class Stats(C.Structure):
                 ('kernel_launches', C.c_uint64), ('n_sites', C.c_int64), ('capacity', C.c_int64),
                 ('rounds', C.c_int32), ('pad_', C.c_int32), ('ms_integrate', C.c_double),
                 ('ms_resample', C.c_double), ('ms_trim', C.c_double), ('ms_arrival', C.c_double),
-                ('ms_total', C.c_double), ('ms_upload', C.c_double)]
+                ('ms_total', C.c_double), ('ms_upload', C.c_double), ('ms_obstacle', C.c_double)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_ if name != 'pad_'}

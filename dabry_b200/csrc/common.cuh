@@ -13,7 +13,7 @@
 #define DABRY_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define DABRY_HD inline
-#define DABRY_HD_NOINLINE
+#define DABRY_HD_NOINLINE inline
 #endif
 
 #define DABRY_MAX_OBSTACLES 8
@@ -45,6 +45,15 @@ DABRY_HD double sub_rn(double a, double b) {
     return __dadd_rn(a, -b);
 #else
     return a - b;
+#endif
+}
+
+// 1 / sqrt(x): the device's rsqrt (<= 1 ulp) instead of a square root followed by a division
+DABRY_HD double inv_sqrt(double x) {
+#if defined(__CUDA_ARCH__)
+    return rsqrt(x);
+#else
+    return 1. / sqrt(x);
 #endif
 }
 

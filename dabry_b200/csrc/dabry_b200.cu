@@ -10,8 +10,17 @@ namespace dabry {
 
 // one thread per work item; the functor (problem constants, site-store pointers) travels as a __grid_constant__
 // kernel parameter so that uniform reads of the problem description hit the constant bank
+template <class F, class = void>
+struct MinBlocks {
+    static constexpr int value = 1;
+};
 template <class F>
-__global__ void __launch_bounds__(F::kThreads) phase_kernel(int64_t n, const __grid_constant__ F f) {
+struct MinBlocks<F, decltype((void) F::kMinBlocks)> {
+    static constexpr int value = F::kMinBlocks;
+};
+
+template <class F>
+__global__ void __launch_bounds__(F::kThreads, MinBlocks<F>::value) phase_kernel(int64_t n, const __grid_constant__ F f) {
     const int64_t i = (int64_t) blockIdx.x * F::kThreads + threadIdx.x;
     if (i < n) f(i);
 }

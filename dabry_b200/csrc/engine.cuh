@@ -19,6 +19,10 @@
 #include "../../include/dabry_b200.h"
 #include "site.cuh"
 
+#ifndef DABRY_INTEGRATE_MIN_BLOCKS
+#define DABRY_INTEGRATE_MIN_BLOCKS 4
+#endif
+
 namespace dabry {
 
 static_assert(sizeof(FieldLeaf) == sizeof(dabry_leaf), "leaf layout");
@@ -107,18 +111,39 @@ struct GhostInitPhase {  // the ghost slot = ring root `ring_index`, evaluated b
 };
 
 template <int FK>
-struct IntegratePhase {
+struct FreeArcPhase {  // the hot kernel: one thread per extremal, free arc with events
     static constexpr int kThreads = 128;
+    static constexpr int kMinBlocks = DABRY_INTEGRATE_MIN_BLOCKS;  // register cap = 65536 / (128 * kMinBlocks)
     ProblemDev P;
-    SolverParams C;
     SiteStore S;
     const int32_t* list;  // null: sites [base, base + n)
     int32_t base, index_t;
     Counters* counters;
+    int32_t* captured;    // -1 / 0 per work item: does the site need the obstacle kernel
     DABRY_HD void operator()(int64_t i) const {
         const int s = list ? list[i] : base + (int) i;
         unsigned attempts = 0, calls = 0;
-        site_integrate<FK>(P, C, S, s, index_t, attempts, calls);
+        site_free_arc<FK>(P, S, s, index_t, attempts, calls);
+        counter_add(&counters->rk_steps, attempts);
+        counter_add(&counters->ivp_calls, calls);
+        captured[i] = (S.arc_from[s] >= 0 && S.obstacle[s] >= 0) ? 0 : -1;
+    }
+};
+
+template <int FK>
+struct ObstacleArcPhase {  // entry side, feasibility and boundary following for the captured extremals
+    static constexpr int kThreads = 64;
+    ProblemDev P;
+    SiteStore S;
+    const int32_t* list;      // the integrate work list (null: base + item)
+    const int32_t* captured;  // dense list of captured work items
+    int32_t base, index_t;
+    Counters* counters;
+    DABRY_HD void operator()(int64_t i) const {
+        const int item = captured[i];
+        const int s = list ? list[item] : base + item;
+        unsigned attempts = 0, calls = 0;
+        site_obstacle_arcs<FK>(P, S, s, index_t, attempts, calls);
         counter_add(&counters->rk_steps, attempts);
         counter_add(&counters->ivp_calls, calls);
     }
@@ -296,9 +321,9 @@ struct PackGridPhase {
     DABRY_HD void operator()(int64_t i) const {
         const int iy = (int) (i % ny);
         const int ix = (int) ((i / ny) % nx);
-        const int k = (int) (i / ((int64_t) ny * nx));
+        const int k = (int) (i / ((int64_t) ny * nx)) - 1;  // record frame f = k + 1, k = -1 .. nt - 1
         double a[6], b[6];
-        node(k, ix, iy, a);
+        node(imax(k, 0), ix, iy, a);
         node(imin(k + 1, nt - 1), ix, iy, b);
         double* o = out + 12 * i;
 #pragma unroll
@@ -474,6 +499,9 @@ public:
         be.free(d_request);
         be.free(d_offset);
         be.free(d_list);
+        be.free(d_captured);
+        be.free(d_cap_offset);
+        be.free(d_cap_list);
         be.free(d_map);
         be.free(d_arr_index);
         be.free(d_arr_cost);
@@ -498,10 +526,12 @@ public:
             return fail(DABRY_ERR_INVALID, "flow grid: need values, nt >= 1, nx >= 3, ny >= 3 (nt == 1 if steady)");
         be.tic();
         const int64_t nodes = (int64_t) nt * nx * ny;
+        const int64_t records = (int64_t) (nt + 1) * nx * ny;
+        if (records >= (int64_t) 1 << 31) return fail(DABRY_ERR_CAPACITY, "flow grid: more than 2^31 records");
         double* d_values = (double*) be.alloc(sizeof(double) * 2 * nodes);
         double* d_grad = grad ? (double*) be.alloc(sizeof(double) * 4 * nodes) : nullptr;
         be.free(d_grid);
-        d_grid = (double*) be.alloc(sizeof(double) * 12 * nodes);
+        d_grid = (double*) be.alloc(sizeof(double) * 12 * records);
         if (!d_values || !d_grid || (grad && !d_grad)) return fail(DABRY_ERR_CAPACITY, "flow grid: out of device memory");
         be.upload(d_values, values, sizeof(double) * 2 * nodes);
         if (grad) be.upload(d_grad, grad, sizeof(double) * 4 * nodes);
@@ -516,9 +546,10 @@ public:
             G.lo[a] = lo[a];
             // (bounds[:, 1] - bounds[:, 0]) / (shape - 1)  (flowfield.py:198-199)
             G.spacing[a] = (a == 0 && !unsteady) ? 1. : (hi[a] - lo[a]) / (double) (n_ax[a] - 1);
+            G.inv_spacing[a] = 1. / G.spacing[a];
         }
         PackGridPhase ph{d_values, d_grad, d_grid, nt, nx, ny, 2 * G.spacing[1], 2 * G.spacing[2]};
-        be.launch(nodes, ph);
+        be.launch(records, ph);
         be.sync();
         be.free(d_values);
         be.free(d_grad);
@@ -567,10 +598,17 @@ public:
         const int64_t n0 = cfg.root_count + has_ghost;
         int64_t cap = cfg.max_sites > 0 ? cfg.max_sites : 2 * n0 + 1024;
         if (cap < n0) cap = n0;
-        free_store(S);
-        memset(&S, 0, sizeof(S));
         n_sites = 0;
-        if (int rc = reserve(cap)) return rc;
+        if (S.capacity >= cap && S.n_time == cfg.n_time) {
+            // same handle solved again: keep the store, restore the NaN controls / empty neighbour links
+            const int64_t cells = (int64_t) cfg.n_time * S.capacity;
+            be.launch(2 * cells, FillF64Phase{(double*) S.ctrl, quiet_nan()});
+            be.launch(cells, FillI32Phase{S.next_nb, -1});
+        } else {
+            free_store(S);
+            memset(&S, 0, sizeof(S));
+            if (int rc = reserve(cap)) return rc;
+        }
         double* d_cost = nullptr;
         if (costates) {
             d_cost = (double*) be.alloc(sizeof(double) * 2 * cfg.root_count);
@@ -596,7 +634,7 @@ public:
         last_new = 0;
         be.zero(d_counters, sizeof(Counters));
         stats.rounds = 0;
-        stats.ms_integrate = stats.ms_resample = stats.ms_trim = stats.ms_arrival = stats.ms_total = 0.;
+        stats.ms_integrate = stats.ms_obstacle = stats.ms_resample = stats.ms_trim = stats.ms_arrival = stats.ms_total = 0.;
         return check();
     }
 
@@ -831,6 +869,10 @@ private:
     int32_t* d_request = nullptr;
     int32_t* d_offset = nullptr;
     int32_t* d_list = nullptr;
+    int32_t* d_captured = nullptr;
+    int32_t* d_cap_offset = nullptr;
+    int32_t* d_cap_list = nullptr;
+    int64_t work_capacity = 0;
     double* d_map = nullptr;
     int32_t* d_arr_index = nullptr;
     double* d_arr_cost = nullptr;
@@ -873,6 +915,20 @@ private:
         return d_scratch;
     }
 
+    int ensure_work(int64_t n) {
+        if (n <= work_capacity) return DABRY_OK;
+        const int64_t cap = n + n / 2 + 1024;
+        be.free(d_captured);
+        be.free(d_cap_offset);
+        be.free(d_cap_list);
+        d_captured = (int32_t*) be.alloc(sizeof(int32_t) * cap);
+        d_cap_offset = (int32_t*) be.alloc(sizeof(int32_t) * cap);
+        d_cap_list = (int32_t*) be.alloc(sizeof(int32_t) * cap);
+        if (!d_captured || !d_cap_offset || !d_cap_list) return fail(DABRY_ERR_CAPACITY, "out of device memory (work)");
+        work_capacity = cap;
+        return DABRY_OK;
+    }
+
     int ensure_aux(int64_t n) {
         if (n <= aux_capacity) return DABRY_OK;
         const int64_t cap = n + n / 2 + 1024;
@@ -912,6 +968,7 @@ private:
         be.free(s.check_next); be.free(s.depth); be.free(s.flags); be.free(s.parent_prev); be.free(s.parent_next);
         be.free(s.created_subframe); be.free(s.valid_first); be.free(s.valid_last); be.free(s.dyadic);
         be.free(s.next_nb); be.free(s.n_target_events); be.free(s.t_target_events); be.free(s.ivp_status);
+        be.free(s.arc_from); be.free(s.enter);
     }
 
     int reserve(int64_t want) {
@@ -948,6 +1005,7 @@ private:
         ok = ok && grow(S.valid_first, oc, cap, 1, 1) && grow(S.valid_last, oc, cap, 1, 1);
         ok = ok && grow(S.dyadic, oc, cap, 1, 1) && grow(S.n_target_events, oc, cap, 1, 1);
         ok = ok && grow(S.t_target_events, oc, cap, 1, DABRY_MAX_TARGET_EVENTS) && grow(S.ivp_status, oc, cap, 1, 1);
+        ok = ok && grow(S.arc_from, oc, cap, 1, 1) && grow(S.enter, oc, cap, 1, 1);
         if (!ok) return fail(DABRY_ERR_CAPACITY, "out of device memory (site store)");
         S.capacity = (int32_t) cap;
         S.n_time = cfg.n_time;
@@ -958,17 +1016,24 @@ private:
     }
 
     int integrate(const int32_t* list, int32_t base, int64_t n, int index_t) {
+        if (int rc = ensure_work(n)) return rc;
         be.tic();
-        if (P.field.kind == FIELD_GRID) {
-            IntegratePhase<FIELD_GRID> ph{P, C, S, list, base, index_t, d_counters};
-            be.launch(n, ph);
-        } else {
-            IntegratePhase<FIELD_PROGRAM> ph{P, C, S, list, base, index_t, d_counters};
-            be.launch(n, ph);
+        if (P.field.kind == FIELD_GRID) be.launch(n, FreeArcPhase<FIELD_GRID>{P, S, list, base, index_t, d_counters, d_captured});
+        else be.launch(n, FreeArcPhase<FIELD_PROGRAM>{P, S, list, base, index_t, d_counters, d_captured});
+        stats.ms_integrate += be.toc();
+        if (C.follow_obstacles) {
+            be.tic();
+            const int64_t n_cap = be.scan_requests(d_captured, n, d_cap_offset, d_cap_list);
+            if (n_cap > 0) {
+                if (P.field.kind == FIELD_GRID)
+                    be.launch(n_cap, ObstacleArcPhase<FIELD_GRID>{P, S, list, d_cap_list, base, index_t, d_counters});
+                else
+                    be.launch(n_cap, ObstacleArcPhase<FIELD_PROGRAM>{P, S, list, d_cap_list, base, index_t, d_counters});
+            }
+            stats.ms_obstacle += be.toc();
         }
         ConnectPhase cp{S, list, base};
         be.launch(n, cp);
-        stats.ms_integrate += be.toc();
         return check();
     }
 

@@ -8,8 +8,8 @@
 // Both are seen through the non-dimensionalising WrapperFF (flowfield.py:518-544); identity parameters
 // (time_origin 0, scales 1, bl 0) reproduce an unwrapped field bit for bit.
 //
-// HBM layout of a grid ("pair records"): for every (k, i, j) one 96-byte record
-//     { (c_k, c_k+1) : c in u, v, du/dx, du/dy, dv/dx, dv/dy }        frame k+1 clipped to nt-1
+// HBM layout of a grid ("pair records"): for every (k, i, j), k = -1 .. nt - 1, one 96-byte record
+//     { (c_max(k,0), c_min(k+1,nt-1)) : c in u, v, du/dx, du/dy, dv/dx, dv/dy }
 // i.e. the two frames a time lerp needs are interleaved, a node is six aligned 16-byte loads, and the two
 // nodes (j, j+1) of a cell edge are one contiguous 192-byte run (y is the fastest grid axis, as in the
 // reference's values[k, i, j, :]).
@@ -47,6 +47,7 @@ struct GridDesc {
     int32_t unsteady;    // 0: 2-D interpolation (flowfield.py:451-452, 466-468); nt == 1
     double lo[3];        // bounds[:, 0] for (t, x, y); lo[0] unused when steady
     double spacing[3];   // (hi - lo) / (n - 1), flowfield.py:198-199
+    double inv_spacing[3];
 };
 
 struct FieldDesc {
@@ -256,42 +257,46 @@ DABRY_HD D2 load_pair(const double* p) {
 
 // Utils.interpolate (misc.py:570-589) on values and grad_values at once.  Weights come from the UNCLIPPED
 // floor; indices lo and lo + 1 are clipped independently to [0, n - 1]; no wrap in longitude.
+//
+// Frame records: record frame f = k + 1 holds (c[max(k, 0)], c[min(k + 1, nt - 1)]) for k = -1 .. nt - 1, so that the
+// clipped pair (lo, hi) of ANY time position is one record and the time lerp needs no select: k < 0 -> both frame 0,
+// k >= nt - 1 -> both frame nt - 1.  Positions use the host-computed reciprocal spacing (one rounding away from the
+// reference's division; continuous in the result).
 DABRY_HD void grid_eval(const GridDesc& G, double t, double x0, double x1, Flow& o) {
     double wt_lo = 1., wt_hi = 0.;
-    int kp = 0;
-    bool t_same = false;
+    int frame = 1;
     if (G.unsteady) {
-        const double pos = (t - G.lo[0]) / G.spacing[0];
+        const double pos = (t - G.lo[0]) * G.inv_spacing[0];
         const double fl = floor(pos);
         wt_hi = pos - fl;
         wt_lo = 1. - wt_hi;
-        const int k = (int) fl;
-        kp = iclamp(k, 0, G.nt - 1);
-        t_same = k < 0;  // both clipped indices are frame 0
+        frame = iclamp((int) fl, -1, G.nt - 1) + 1;
     }
-    const double px = (x0 - G.lo[1]) / G.spacing[1];
-    const double py = (x1 - G.lo[2]) / G.spacing[2];
+    const double px = (x0 - G.lo[1]) * G.inv_spacing[1];
+    const double py = (x1 - G.lo[2]) * G.inv_spacing[2];
     const double fx = floor(px), fy = floor(py);
     const double wx_hi = px - fx, wy_hi = py - fy;
     const double wx_lo = 1. - wx_hi, wy_lo = 1. - wy_hi;
-    const int i0 = iclamp((int) fx, 0, G.nx - 1), i1 = iclamp((int) fx + 1, 0, G.nx - 1);
-    const int j0 = iclamp((int) fy, 0, G.ny - 1), j1 = iclamp((int) fy + 1, 0, G.ny - 1);
-    const int64_t plane = (int64_t) kp * G.nx;
-    const double* n00 = G.data + ((plane + i0) * G.ny + j0) * 12;
-    const double* n01 = G.data + ((plane + i0) * G.ny + j1) * 12;
-    const double* n10 = G.data + ((plane + i1) * G.ny + j0) * 12;
-    const double* n11 = G.data + ((plane + i1) * G.ny + j1) * 12;
+    const int ix = (int) fx, iy = (int) fy;
+    const int i0 = iclamp(ix, 0, G.nx - 1), i1 = iclamp(ix + 1, 0, G.nx - 1);
+    const int j0 = iclamp(iy, 0, G.ny - 1), j1 = iclamp(iy + 1, 0, G.ny - 1);
+    // record indices fit 32 bits (checked at upload); one 64-bit multiply per node for the byte offset
+    const unsigned row0 = ((unsigned) frame * (unsigned) G.nx + (unsigned) i0) * (unsigned) G.ny;
+    const unsigned row1 = ((unsigned) frame * (unsigned) G.nx + (unsigned) i1) * (unsigned) G.ny;
+    const double* n00 = G.data + (size_t) (row0 + j0) * 12;
+    const double* n01 = G.data + (size_t) (row0 + j1) * 12;
+    const double* n10 = G.data + (size_t) (row1 + j0) * 12;
+    const double* n11 = G.data + (size_t) (row1 + j1) * 12;
+    // corner weights (w_t * w_x) * w_y in the reference; here the time factor is applied per node first
     const double w00 = wx_lo * wy_lo, w01 = wx_lo * wy_hi, w10 = wx_hi * wy_lo, w11 = wx_hi * wy_hi;
     double acc[6];
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
         const D2 a = load_pair(n00 + 2 * c), b = load_pair(n01 + 2 * c);
         const D2 d = load_pair(n10 + 2 * c), e = load_pair(n11 + 2 * c);
-        const double ta = wt_lo * a.x + wt_hi * (t_same ? a.x : a.y);
-        const double tb = wt_lo * b.x + wt_hi * (t_same ? b.x : b.y);
-        const double td = wt_lo * d.x + wt_hi * (t_same ? d.x : d.y);
-        const double te = wt_lo * e.x + wt_hi * (t_same ? e.x : e.y);
-        acc[c] = ((w00 * ta + w01 * tb) + w10 * td) + w11 * te;
+        const double lo = ((w00 * a.x + w01 * b.x) + w10 * d.x) + w11 * e.x;
+        const double hi = ((w00 * a.y + w01 * b.y) + w10 * d.y) + w11 * e.y;
+        acc[c] = wt_lo * lo + wt_hi * hi;
     }
     o.w0 = acc[0];
     o.w1 = acc[1];

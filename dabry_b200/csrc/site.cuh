@@ -23,7 +23,7 @@ struct Control {
     double u0, u1;
 };
 
-enum SiteFlags : int32_t { SITE_GHOST = 1, SITE_CONNECTED = 2 };
+enum SiteFlags : int32_t { SITE_GHOST = 1, SITE_CONNECTED = 2, SITE_PENDING_ENTRY = 4 };
 
 struct SiteStore {
     int32_t n_time;
@@ -58,6 +58,8 @@ struct SiteStore {
     int32_t* n_target_events;   // events['target'] (non terminal): count and the first few roots
     double* t_target_events;    // [capacity][DABRY_MAX_TARGET_EVENTS]
     int32_t* ivp_status;        // status of the last solve_ivp call of the site (diagnostics)
+    int32_t* arc_from;          // grid index the current integrate call started from (-1: nothing to do)
+    Sample* enter;              // augmented state at the obstacle entry root, between the two integrate kernels
     // time-major addressing: consecutive sites are consecutive in memory at a given grid index, so that a warp
     // of extremals advancing in lockstep writes (and the resampling scan reads) fully coalesced rows
     DABRY_HD int64_t at(int s, int k) const { return (int64_t) k * capacity + s; }
@@ -104,6 +106,7 @@ DABRY_HD void site_reset(const SiteStore& S, int s) {
     S.dyadic[s] = 0;
     S.n_target_events[s] = 0;
     S.ivp_status[s] = 0;
+    S.arc_from[s] = -1;
     // next_nb rows are filled with -1 when the storage is allocated; slots are never recycled
 }
 
@@ -189,82 +192,98 @@ struct ConstrSink {
     }
 };
 
+// integrate_site_to_target_index is split in two device procedures so that the hot kernel (free arcs: every
+// extremal, ~all of the RK work) stays small enough for the instruction cache and the rare, branchy obstacle
+// handling runs in a second kernel over the captured sites only.
+//
+// Part A - the free arc (solver_ef.py:482-504): solve_ivp on the augmented system with the target / obstacle events.
+// A terminal obstacle event leaves the entry record (obstacle, t_enter_obs, index_t_obs, state at entry) for part B.
 template <int FK>
-DABRY_HD void site_integrate(const ProblemDev& P, const SolverParams& C, const SiteStore& S, int s, int index_t,
-                             unsigned& n_attempts, unsigned& n_calls) {
+DABRY_HD void site_free_arc(const ProblemDev& P, const SiteStore& S, int s, int index_t, unsigned& n_attempts,
+                            unsigned& n_calls) {
     const int idx0 = site_index_t(S, s);
+    S.arc_from[s] = -1;
     if (idx0 >= index_t) return;
     const int n = index_t - idx0 + 1;
     if (n <= 1) return;
+    S.arc_from[s] = idx0;
+    if (site_in_obs_at(S, s, idx0)) return;
+    const Sample y0s = S.xp[S.at(s, idx0)];
+    const double y0[4] = {y0s.x0, y0s.x1, y0s.p0, y0s.p1};
+    const EvalGrid grid = make_eval_grid(S.times[idx0], S.times[index_t], n, 1);
+    AugRhs<FK> rhs{P};
+    FreeEvents ev{P, S, s};
+    FreeSink sink{S, s, idx0};
+    IvpResult<4> res;
+    solve_ivp<4>(rhs, ev, sink, grid.at(0), grid.at(n - 1), y0, grid, P.max_step, P.rtol, P.atol, res, n_attempts);
+    ++n_calls;
+    S.ivp_status[s] = res.status;
+    S.n_samples[s] += res.n_emitted;
+    if (res.status == IVP_TERMINATED) {
+        S.t_enter_obs[s] = res.t_term;
+        S.obstacle[s] = res.term_event;
+        S.index_t_obs[s] = idx0 + res.n_emitted + 1;  // site.index_t + len(traj_free) + 1 (:516)
+        S.enter[s] = Sample{res.y_term[0], res.y_term[1], res.y_term[2], res.y_term[3]};
+        S.flags[s] |= SITE_PENDING_ENTRY;
+    }
+}
+
+// Part B - obstacle entry and boundary following (solver_ef.py:506-576) for a site captured during part A of this
+// call, or captured earlier and not yet at index_t.
+template <int FK>
+DABRY_HD void site_obstacle_arcs(const ProblemDev& P, const SiteStore& S, int s, int index_t, unsigned& n_attempts,
+                                 unsigned& n_calls) {
+    const int idx0 = S.arc_from[s];
+    if (idx0 < 0 || S.obstacle[s] < 0) return;
+    const int n = index_t - idx0 + 1;
     const double t_start = S.times[idx0], t_end = S.times[index_t];
-    if (!site_in_obs_at(S, s, idx0)) {
-        const Sample y0s = S.xp[S.at(s, idx0)];
-        const double y0[4] = {y0s.x0, y0s.x1, y0s.p0, y0s.p1};
+    const int obs = S.obstacle[s] - 1;  // index into P.obstacles
+    if (S.flags[s] & SITE_PENDING_ENTRY) {
+        S.flags[s] &= ~SITE_PENDING_ENTRY;
         const EvalGrid grid = make_eval_grid(t_start, t_end, n, 1);
-        AugRhs<FK> rhs{P};
-        FreeEvents ev{P, S, s};
-        FreeSink sink{S, s, idx0};
-        IvpResult<4> res;
-        solve_ivp<4>(rhs, ev, sink, grid.at(0), grid.at(n - 1), y0, grid, P.max_step, P.rtol, P.atol, res,
-                     n_attempts);
-        ++n_calls;
-        S.ivp_status[s] = res.status;
-        const int n_free = res.n_emitted;
-        S.n_samples[s] += n_free;
-        if (res.status == IVP_TERMINATED) {
-            const int obs = res.term_event - 1;  // index into P.obstacles
-            const double t_enter = res.t_term;
-            S.t_enter_obs[s] = t_enter;
-            S.obstacle[s] = res.term_event;
-            S.index_t_obs[s] = idx0 + n_free + 1;
-            if (!C.follow_obstacles) return;
-            const double xc0 = res.y_term[0], xc1 = res.y_term[1];
-            double g0, g1;
-            obstacle_grad(P.obstacles[obs], xc0, xc1, g0, g1);
-            const double pn = sqrt(res.y_term[2] * res.y_term[2] + res.y_term[3] * res.y_term[3]);
-            double v0, v1;
-            dyn_value<FK>(P, t_enter, xc0, xc1, -res.y_term[2] / pn, -res.y_term[3] / pn, v0, v1);
-            const bool trigo = (g0 * v1 - g1 * v0) >= 0.;  // np.cross(d_value, dyn.value) (solver_ef.py:519-523)
-            S.trigo[s] = trigo ? 1 : 0;
-            const double sign = trigo ? 1. : -1.;
-            const double d0 = -sign * g1, d1 = sign * g0;
-            Flow f;
-            field_eval<FK>(P.field, t_enter, xc0, xc1, f);
-            if (possible_direction(f.w0, f.w1, d0, d1, P.srf)) {
-                // t_eval[t_eval > t_enter_obs][0]  (solver_ef.py:528-530)
-                int jn = n_free + 1;
-                while (jn < n && !(grid.at(jn) > t_enter)) ++jn;
-                if (jn < n) {
-                    const double t_next = grid.at(jn);
-                    EvalGrid one;
-                    one.t_start = t_next;
-                    one.t_end = t_next;
-                    one.step = 0.;
-                    one.n = 1;
-                    one.first = 0;
-                    ConstrRhs<FK> crhs{P, obs, trigo};
-                    NoEvents nev;
-                    ConstrSink<FK> csink{P, S, s, idx0 + n_free + 1, obs, trigo};
-                    IvpResult<2> r2;
-                    const double x0c[2] = {xc0, xc1};
-                    solve_ivp<2>(crhs, nev, csink, t_enter, t_next, x0c, one, P.max_step, P.rtol, P.atol, r2,
-                                 n_attempts);
-                    ++n_calls;
-                    if (r2.n_emitted == 0) S.closure[s] = CLOSURE_IMPOSSIBLE_OBS_TRACKING;
-                    S.n_samples[s] += r2.n_emitted;
-                } else {
-                    S.closure[s] = CLOSURE_IMPOSSIBLE_OBS_TRACKING;
-                }
-            } else {
-                S.closure[s] = CLOSURE_IMPOSSIBLE_OBS_TRACKING;
+        const int n_free = S.index_t_obs[s] - 1 - idx0;
+        const double t_enter = S.t_enter_obs[s];
+        const Sample ye = S.enter[s];
+        double g0, g1;
+        obstacle_grad(P.obstacles[obs], ye.x0, ye.x1, g0, g1);
+        const double pn = sqrt(ye.p0 * ye.p0 + ye.p1 * ye.p1);
+        double v0, v1;
+        dyn_value<FK>(P, t_enter, ye.x0, ye.x1, -ye.p0 / pn, -ye.p1 / pn, v0, v1);
+        const bool trigo = (g0 * v1 - g1 * v0) >= 0.;  // np.cross(d_value, dyn.value) (solver_ef.py:519-523)
+        S.trigo[s] = trigo ? 1 : 0;
+        const double sign = trigo ? 1. : -1.;
+        const double d0 = -sign * g1, d1 = sign * g0;
+        Flow f;
+        field_eval<FK>(P.field, t_enter, ye.x0, ye.x1, f);
+        bool tracked = false;
+        if (possible_direction(f.w0, f.w1, d0, d1, P.srf)) {
+            // t_eval[t_eval > t_enter_obs][0]  (solver_ef.py:528-530)
+            int jn = n_free + 1;
+            while (jn < n && !(grid.at(jn) > t_enter)) ++jn;
+            if (jn < n) {
+                const double t_next = grid.at(jn);
+                EvalGrid one;
+                one.t_start = t_next;
+                one.t_end = t_next;
+                one.step = 0.;
+                one.n = 1;
+                one.first = 0;
+                ConstrRhs<FK> crhs{P, obs, trigo};
+                NoEvents nev;
+                ConstrSink<FK> csink{P, S, s, idx0 + n_free + 1, obs, trigo};
+                IvpResult<2> r2;
+                const double x0c[2] = {ye.x0, ye.x1};
+                solve_ivp<2>(crhs, nev, csink, t_enter, t_next, x0c, one, P.max_step, P.rtol, P.atol, r2, n_attempts);
+                ++n_calls;
+                tracked = r2.n_emitted > 0;
+                S.n_samples[s] += r2.n_emitted;
             }
         }
+        if (!tracked) S.closure[s] = CLOSURE_IMPOSSIBLE_OBS_TRACKING;
     }
-    if (!C.follow_obstacles) return;
-    // Either the site reached index_t, or it is short of it and (if captured) slides along the obstacle
+    // Either the site reached index_t, or it is short of it and slides along the obstacle (:556-574)
     const int idx1 = site_index_t(S, s);
-    if (idx1 < index_t && S.obstacle[s] >= 0) {
-        const int obs = S.obstacle[s] - 1;
+    if (idx1 < index_t) {
         const bool trigo = S.trigo[s] != 0;
         const int j0 = idx1 - idx0;
         const EvalGrid grid = make_eval_grid(t_start, t_end, n, j0 + 1);

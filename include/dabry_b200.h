@@ -144,8 +144,9 @@ typedef struct dabry_stats {
     int64_t capacity;
     int32_t rounds;
     int32_t pad_;
-    double ms_integrate, ms_resample, ms_trim, ms_arrival, ms_total;   /* device time by phase (CUDA events) */
+    double ms_integrate, ms_resample, ms_trim, ms_arrival, ms_total;   /* device time by phase (CUDA events); ms_integrate = free-arc kernel */
     double ms_upload;        /* flow grid repack + derivative kernels */
+    double ms_obstacle;      /* obstacle entry + boundary-following kernel (captured extremals only) */
 } dabry_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------ */
