@@ -220,6 +220,10 @@ public:
         chk(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, cudaMemcpyDeviceToDevice, stream_), "D2D copy");
     }
     void sync() { chk(cudaStreamSynchronize(stream_), "stream sync"); }
+    // the problem description of the calling engine -> constant memory, ordered on the engine's stream
+    void set_problem(const ProblemDev& P) {
+        chk(cudaMemcpyToSymbolAsync(c_problem, &P, sizeof(ProblemDev), 0, cudaMemcpyHostToDevice, stream_), "bind problem");
+    }
 
     template <class F>
     void launch(int64_t n, const F& f) {

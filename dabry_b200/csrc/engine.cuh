@@ -114,7 +114,6 @@ template <int FK>
 struct FreeArcPhase {  // the hot kernel: one thread per extremal, free arc with events
     static constexpr int kThreads = 128;
     static constexpr int kMinBlocks = DABRY_INTEGRATE_MIN_BLOCKS;  // register cap = 65536 / (128 * kMinBlocks)
-    ProblemDev P;
     SiteStore S;
     const int32_t* list;  // null: sites [base, base + n)
     int32_t base, index_t;
@@ -123,7 +122,7 @@ struct FreeArcPhase {  // the hot kernel: one thread per extremal, free arc with
     DABRY_HD void operator()(int64_t i) const {
         const int s = list ? list[i] : base + (int) i;
         unsigned attempts = 0, calls = 0;
-        site_free_arc<FK>(P, S, s, index_t, attempts, calls);
+        site_free_arc<FK>(problem(), S, s, index_t, attempts, calls);
         counter_add(&counters->rk_steps, attempts);
         counter_add(&counters->ivp_calls, calls);
         captured[i] = (S.arc_from[s] >= 0 && S.obstacle[s] >= 0) ? 0 : -1;
@@ -132,8 +131,8 @@ struct FreeArcPhase {  // the hot kernel: one thread per extremal, free arc with
 
 template <int FK>
 struct ObstacleArcPhase {  // entry side, feasibility and boundary following for the captured extremals
-    static constexpr int kThreads = 64;
-    ProblemDev P;
+    static constexpr int kThreads = 128;
+    static constexpr int kMinBlocks = 3;
     SiteStore S;
     const int32_t* list;      // the integrate work list (null: base + item)
     const int32_t* captured;  // dense list of captured work items
@@ -143,7 +142,7 @@ struct ObstacleArcPhase {  // entry side, feasibility and boundary following for
         const int item = captured[i];
         const int s = list ? list[item] : base + item;
         unsigned attempts = 0, calls = 0;
-        site_obstacle_arcs<FK>(P, S, s, index_t, attempts, calls);
+        site_obstacle_arcs<FK>(problem(), S, s, index_t, attempts, calls);
         counter_add(&counters->rk_steps, attempts);
         counter_add(&counters->ivp_calls, calls);
     }
@@ -159,14 +158,13 @@ struct ConnectPhase {  // connect_to_parents (solver_ef.py:690-699)
 
 struct ResamplePhase {  // compute_new_sites, one site of the loop at solver_ef.py:634-661
     static constexpr int kThreads = 256;
-    ProblemDev P;
     SolverParams C;
     SiteStore S;
     int32_t index_t_hi;
     int32_t* request;
     DABRY_HD void operator()(int64_t i) const {
         const int s = (int) i;
-        request[s] = (S.flags[s] & SITE_GHOST) ? -1 : site_resample(P, C, S, s, index_t_hi);
+        request[s] = (S.flags[s] & SITE_GHOST) ? -1 : site_resample(problem(), C, S, s, index_t_hi);
     }
 };
 
@@ -185,24 +183,22 @@ struct SpawnPhase {  // site_from_parents + dict insertion order (solver_ef.py:6
 
 struct TrimDistancePhase {
     static constexpr int kThreads = 256;
-    ProblemDev P;
     SolverParams C;
     SiteStore S;
     DABRY_HD void operator()(int64_t i) const {
-        if (!(S.flags[i] & SITE_GHOST)) site_trim_distance(P, C, S, (int) i);
+        if (!(S.flags[i] & SITE_GHOST)) site_trim_distance(problem(), C, S, (int) i);
     }
 };
 
 struct ArrivalPhase {
     static constexpr int kThreads = 256;
-    ProblemDev P;
     SiteStore S;
     int32_t* arr_index;
     double* arr_cost;
     DABRY_HD void operator()(int64_t i) const {
         double c = 0.;
         int k = -1;
-        if (!(S.flags[i] & SITE_GHOST)) k = site_arrival(P, S, (int) i, c);
+        if (!(S.flags[i] & SITE_GHOST)) k = site_arrival(problem(), S, (int) i, c);
         arr_index[i] = k;
         arr_cost[i] = k >= 0 ? c : INFINITY;
     }
@@ -261,24 +257,22 @@ struct TrimPhase {  // SolverEFTrimming.trim, loop at solver_ef.py:831-841
 template <int FK>
 struct EvalRhsPhase {
     static constexpr int kThreads = 128;
-    ProblemDev P;
     const double* t;
     const double* y;
     double* dy;
-    DABRY_HD void operator()(int64_t i) const { rhs_aug<FK>(P, t[i], y + 4 * i, dy + 4 * i); }
+    DABRY_HD void operator()(int64_t i) const { rhs_aug<FK>(problem(), t[i], y + 4 * i, dy + 4 * i); }
 };
 
 template <int FK>
 struct EvalFlowPhase {
     static constexpr int kThreads = 128;
-    ProblemDev P;
     const double* t;
     const double* x;
     double* w;
     double* jac;
     DABRY_HD void operator()(int64_t i) const {
         Flow f;
-        field_eval<FK>(P.field, t[i], x[2 * i], x[2 * i + 1], f);
+        field_eval<FK>(problem().field, t[i], x[2 * i], x[2 * i + 1], f);
         w[2 * i] = f.w0;
         w[2 * i + 1] = f.w1;
         jac[4 * i] = f.j00;
@@ -454,7 +448,7 @@ class Engine {
 public:
     B be;
     dabry_config cfg;
-    ProblemDev P;
+    ProblemDev P;  // host copy; bound to the device's constant memory by bind()
     SolverParams C;
     SiteStore S;
     std::string err;
@@ -589,6 +583,7 @@ public:
 
     // ---- solve ----
     int setup(int variant_, const double* costates) {
+        bind();
         if (P.field.kind < 0) return fail(DABRY_ERR_INVALID, "no flow field set");
         if (cfg.root_count < 1 || cfg.root_offset < 0 || cfg.root_offset + cfg.root_count > cfg.n_roots)
             return fail(DABRY_ERR_INVALID, "bad root range");
@@ -644,6 +639,7 @@ public:
     }
 
     int step_integrate() {
+        bind();
         if (variant == DABRY_TRIMMING) return fail(DABRY_ERR_INVALID, "step_integrate: resampling/simple only");
         if (shoot_end > shoot_begin) {
             if (int rc = integrate(nullptr, shoot_begin, shoot_end - shoot_begin, cfg.n_time - 1)) return rc;
@@ -652,12 +648,13 @@ public:
     }
 
     int step_resample() {
+        bind();
         shoot_begin = shoot_end = (int32_t) n_sites;
         if (variant == DABRY_RESAMPLING) {
             if (int rc = resample(cfg.n_time - 1, 0)) return rc;
             be.tic();
             if (C.ff_max_norm > 1e-8) {  // not np.isclose(max_norm, 0) (solver_ef.py:595)
-                TrimDistancePhase td{P, C, S};
+                TrimDistancePhase td{C, S};
                 be.launch(n_sites, td);
             }
             stats.ms_resample += be.toc();
@@ -675,6 +672,7 @@ public:
 
     // SolverEFTrimming.step (solver_ef.py:802-817)
     int step_trimming() {
+        bind();
         const int q = cfg.n_index_per_subframe;
         const int next = imin((i_subframe + 1) * q, cfg.n_time);  // index_t_next_subframe (:792-794)
         const int target = next - 1;
@@ -701,9 +699,10 @@ public:
     }
 
     int finish() {
+        bind();
         if (int rc = ensure_aux(n_sites)) return rc;
         be.tic();
-        ArrivalPhase ap{P, S, d_arr_index, d_arr_cost};
+        ArrivalPhase ap{S, d_arr_index, d_arr_cost};
         be.launch(n_sites, ap);
         // warp-level min reduction of the arrival cost, then of the slot among the minimisers (lowest slot wins)
         solution_cost = be.min_f64(d_arr_cost, n_sites);
@@ -787,6 +786,7 @@ public:
     }
 
     int get_cost_map(int full, double* out) {
+        bind();
         if (full) {
             if (int rc = build_cost_map(0, cfg.n_time - 1, 1, 0, 0, 0)) return rc;
         }
@@ -833,24 +833,26 @@ public:
 
     // ---- evaluation hooks ----
     int eval_rhs(int64_t n, const double* t, const double* y, double* dy) {
+        bind();
         if (P.field.kind < 0) return fail(DABRY_ERR_INVALID, "no flow field set");
         double* d = (double*) scratch(sizeof(double) * n * 9);
         if (!d) return fail(DABRY_ERR_CAPACITY, "out of device memory");
         be.upload(d, t, sizeof(double) * n);
         be.upload(d + n, y, sizeof(double) * 4 * n);
-        if (P.field.kind == FIELD_GRID) be.launch(n, EvalRhsPhase<FIELD_GRID>{P, d, d + n, d + 5 * n});
-        else be.launch(n, EvalRhsPhase<FIELD_PROGRAM>{P, d, d + n, d + 5 * n});
+        if (P.field.kind == FIELD_GRID) be.launch(n, EvalRhsPhase<FIELD_GRID>{d, d + n, d + 5 * n});
+        else be.launch(n, EvalRhsPhase<FIELD_PROGRAM>{d, d + n, d + 5 * n});
         be.download(dy, d + 5 * n, sizeof(double) * 4 * n);
         return check();
     }
     int eval_flow(int64_t n, const double* t, const double* x, double* w, double* jac) {
+        bind();
         if (P.field.kind < 0) return fail(DABRY_ERR_INVALID, "no flow field set");
         double* d = (double*) scratch(sizeof(double) * n * 9);
         if (!d) return fail(DABRY_ERR_CAPACITY, "out of device memory");
         be.upload(d, t, sizeof(double) * n);
         be.upload(d + n, x, sizeof(double) * 2 * n);
-        if (P.field.kind == FIELD_GRID) be.launch(n, EvalFlowPhase<FIELD_GRID>{P, d, d + n, d + 3 * n, d + 5 * n});
-        else be.launch(n, EvalFlowPhase<FIELD_PROGRAM>{P, d, d + n, d + 3 * n, d + 5 * n});
+        if (P.field.kind == FIELD_GRID) be.launch(n, EvalFlowPhase<FIELD_GRID>{d, d + n, d + 3 * n, d + 5 * n});
+        else be.launch(n, EvalFlowPhase<FIELD_PROGRAM>{d, d + n, d + 3 * n, d + 5 * n});
         be.download(w, d + 3 * n, sizeof(double) * 2 * n);
         be.download(jac, d + 5 * n, sizeof(double) * 4 * n);
         return check();
@@ -900,6 +902,8 @@ private:
         F.scaler_speed = w ? w->scaler_speed : 1.;
         F.scaler_dspeed = w ? w->scaler_dspeed : 1.;
     }
+
+    void bind() { be.set_problem(P); }
 
     int check() {
         if (!be.ok()) return fail(DABRY_ERR_CUDA, be.error());
@@ -1018,17 +1022,17 @@ private:
     int integrate(const int32_t* list, int32_t base, int64_t n, int index_t) {
         if (int rc = ensure_work(n)) return rc;
         be.tic();
-        if (P.field.kind == FIELD_GRID) be.launch(n, FreeArcPhase<FIELD_GRID>{P, S, list, base, index_t, d_counters, d_captured});
-        else be.launch(n, FreeArcPhase<FIELD_PROGRAM>{P, S, list, base, index_t, d_counters, d_captured});
+        if (P.field.kind == FIELD_GRID) be.launch(n, FreeArcPhase<FIELD_GRID>{S, list, base, index_t, d_counters, d_captured});
+        else be.launch(n, FreeArcPhase<FIELD_PROGRAM>{S, list, base, index_t, d_counters, d_captured});
         stats.ms_integrate += be.toc();
         if (C.follow_obstacles) {
             be.tic();
             const int64_t n_cap = be.scan_requests(d_captured, n, d_cap_offset, d_cap_list);
             if (n_cap > 0) {
                 if (P.field.kind == FIELD_GRID)
-                    be.launch(n_cap, ObstacleArcPhase<FIELD_GRID>{P, S, list, d_cap_list, base, index_t, d_counters});
+                    be.launch(n_cap, ObstacleArcPhase<FIELD_GRID>{S, list, d_cap_list, base, index_t, d_counters});
                 else
-                    be.launch(n_cap, ObstacleArcPhase<FIELD_PROGRAM>{P, S, list, d_cap_list, base, index_t, d_counters});
+                    be.launch(n_cap, ObstacleArcPhase<FIELD_PROGRAM>{S, list, d_cap_list, base, index_t, d_counters});
             }
             stats.ms_obstacle += be.toc();
         }
@@ -1041,7 +1045,7 @@ private:
     int resample(int index_t_hi, int subframe) {
         if (int rc = ensure_aux(n_sites)) return rc;
         be.tic();
-        ResamplePhase rp{P, C, S, index_t_hi, d_request};
+        ResamplePhase rp{C, S, index_t_hi, d_request};
         be.launch(n_sites, rp);
         const int64_t n_new = be.scan_requests(d_request, n_sites, d_offset, nullptr);
         if (n_new > 0) {

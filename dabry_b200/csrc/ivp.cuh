@@ -76,73 +76,70 @@ DABRY_HD void solve_ivp(const Rhs& rhs, Events& events, Sink& sink, double t0, d
         }
         const double t_old = S.t_old;
         double t = S.t;
-        Dense<N> D;
-        bool have_dense = false;
         bool terminate = false;
-        if (ne > 0) {
-            double g_new[DABRY_MAX_EVENTS];
-            int act[DABRY_MAX_EVENTS];
-            int na = 0;
-            for (int e = 0; e < ne; ++e) {
-                g_new[e] = events.value(e, t, S.y);
-                if (g[e] >= 0. && g_new[e] <= 0.) act[na++] = e;
+        int act[DABRY_MAX_EVENTS];
+        int na = 0;
+        for (int e = 0; e < ne; ++e) {
+            const double g_new = events.value(e, t, S.y);
+            if (g[e] >= 0. && g_new <= 0.) act[na++] = e;
+            g[e] = g_new;
+        }
+        // the local interpolant is needed for event roots and for the t_eval samples inside this step; it is built
+        // at ONE place so that the stage values stay in registers (truncation by a terminal event only removes samples)
+        const bool sample_due = eval_i < grid.n && grid.at(eval_i) <= t;
+        if (na == 0 && !sample_due) continue;
+        Dense<N> D;
+        rk_dense<N>(S, D);
+        if (na > 0) {
+            // rare path: a copy of the interpolant goes to local memory for the root finder, D itself does not
+            const Dense<N> Dev = D;
+            double roots[DABRY_MAX_EVENTS];
+            bool any_terminal = false;
+            for (int a = 0; a < na; ++a) {
+                const int e = act[a];
+                roots[a] = brentq([&](double tt) {
+                    double yy[N];
+                    dense_eval<N>(Dev, tt, yy);
+                    return events.value(e, tt, yy);
+                }, t_old, t);
+                any_terminal = any_terminal || events.terminal(e);
             }
-            if (na > 0) {
-                rk_dense<N>(S, D);
-                have_dense = true;
-                double roots[DABRY_MAX_EVENTS];
-                bool any_terminal = false;
-                for (int a = 0; a < na; ++a) {
+            int keep = na;
+            if (any_terminal) {
+                // argsort(roots) on a tiny array (insertion sort, stable), cut after the first terminal
+                for (int a = 1; a < na; ++a) {
+                    const double r = roots[a];
                     const int e = act[a];
-                    roots[a] = brentq([&](double tt) {
-                        double yy[N];
-                        dense_eval<N>(D, tt, yy);
-                        return events.value(e, tt, yy);
-                    }, t_old, t);
-                    any_terminal = any_terminal || events.terminal(e);
-                }
-                int keep = na;
-                if (any_terminal) {
-                    // argsort(roots) on a tiny array (insertion sort, stable), cut after the first terminal
-                    for (int a = 1; a < na; ++a) {
-                        const double r = roots[a];
-                        const int e = act[a];
-                        int b = a - 1;
-                        while (b >= 0 && roots[b] > r) {
-                            roots[b + 1] = roots[b];
-                            act[b + 1] = act[b];
-                            --b;
-                        }
-                        roots[b + 1] = r;
-                        act[b + 1] = e;
+                    int b = a - 1;
+                    while (b >= 0 && roots[b] > r) {
+                        roots[b + 1] = roots[b];
+                        act[b + 1] = act[b];
+                        --b;
                     }
-                    for (int a = 0; a < na; ++a)
-                        if (events.terminal(act[a])) {
-                            keep = a + 1;
-                            break;
-                        }
-                    terminate = true;
+                    roots[b + 1] = r;
+                    act[b + 1] = e;
                 }
-                for (int a = 0; a < keep; ++a) events.record(act[a], roots[a]);
-                if (terminate) {
-                    res.status = IVP_TERMINATED;
-                    res.term_event = act[keep - 1];
-                    t = roots[keep - 1];
-                    res.t_term = t;
-                    dense_eval<N>(D, t, res.y_term);
-                    finished = true;
-                }
+                for (int a = 0; a < na; ++a)
+                    if (events.terminal(act[a])) {
+                        keep = a + 1;
+                        break;
+                    }
+                terminate = true;
             }
-            for (int e = 0; e < ne; ++e) g[e] = g_new[e];
+            for (int a = 0; a < keep; ++a) events.record(act[a], roots[a]);
+            if (terminate) {
+                res.status = IVP_TERMINATED;
+                res.term_event = act[keep - 1];
+                t = roots[keep - 1];
+                res.t_term = t;
+                dense_eval<N>(Dev, t, res.y_term);
+                finished = true;
+            }
         }
         // t_eval values <= t that were not emitted yet
         while (eval_i < grid.n) {
             const double te = grid.at(eval_i);
             if (!(te <= t)) break;
-            if (!have_dense) {
-                rk_dense<N>(S, D);
-                have_dense = true;
-            }
             double yy[N];
             dense_eval<N>(D, te, yy);
             sink.emit(eval_i, te, yy);

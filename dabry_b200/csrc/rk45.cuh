@@ -165,7 +165,7 @@ struct Dense {
 };
 
 template <int N>
-DABRY_HD_NOINLINE void rk_dense(const RkState<N>& S, Dense<N>& D) {
+DABRY_HD void rk_dense(const RkState<N>& S, Dense<N>& D) {
     D.t_old = S.t_old;
     D.h = S.t - S.t_old;
 #pragma unroll

@@ -33,6 +33,7 @@ public:
         for (size_t r = 0; r < rows; ++r) memcpy((char*) dst + r * dpitch, (const char*) src + r * spitch, width);
     }
     void sync() {}
+    void set_problem(const ProblemDev& P) { g_problem = P; }
     template <class F>
     void launch(int64_t n, const F& f) {
         ++launches_;
