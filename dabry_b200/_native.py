@@ -63,7 +63,7 @@ SITE_RECORD_DTYPE = np.dtype([
     ('dyadic', np.int64), ('index_t_init', np.int32), ('n_samples', np.int32), ('closure', np.int32),
     ('neuter', np.int32), ('index_neutered', np.int32), ('obstacle', np.int32), ('index_t_obs', np.int32),
     ('obs_trigo', np.int32), ('index_t_check_next', np.int32), ('depth', np.int32), ('parent_prev', np.int32),
-    ('parent_next', np.int32), ('n_target_events', np.int32), ('ivp_status', np.int32),
+    ('parent_next', np.int32), ('n_target_events', np.int32), ('ivp_status', np.int32), ('flags', np.int32), ('pad_', np.int32),
     ('t_enter_obs', np.float64), ('cost0', np.float64), ('t_target_events', np.float64, (MAX_TARGET_EVENTS,)),
 ], align=True)
 
@@ -107,6 +107,7 @@ SIGNATURES = {
     'dabry_get_solution': (C.c_int, [_H, C.POINTER(C.c_int64), c_double_p]),
     'dabry_get_cost_map': (C.c_int, [_H, C.c_int32, c_double_p]),
     'dabry_get_stats': (C.c_int, [_H, C.POINTER(Stats)]),
+    'dabry_get_flow_max_norm': (C.c_int, [_H, c_double_p]),
     'dabry_boundary_doubles': (C.c_int, [_H, C.POINTER(C.c_int64)]),
     'dabry_export_boundary': (C.c_int, [_H, c_double_p]),
     'dabry_import_boundary': (C.c_int, [_H, c_double_p]),
@@ -238,6 +239,11 @@ class Handle:
         s = Stats()
         self.call('dabry_get_stats', C.byref(s))
         return s.as_dict()
+
+    def flow_max_norm(self):
+        v = C.c_double()
+        self.call('dabry_get_flow_max_norm', C.byref(v))
+        return v.value
 
     def cost_map(self, nx, ny, full=False):
         out = np.empty((nx, ny))

@@ -166,6 +166,13 @@ int dabry_get_stats(dabry_solver* h, dabry_stats* out) {
     return E.get_stats(out);
 }
 
+int dabry_get_flow_max_norm(dabry_solver* h, double* out) {
+    DABRY_GUARD(h);
+    if (!out) return DABRY_ERR_INVALID;
+    *out = E.flow_max_norm;
+    return DABRY_OK;
+}
+
 int dabry_boundary_doubles(dabry_solver* h, int64_t* n) {
     DABRY_GUARD(h);
     if (!n) return DABRY_ERR_INVALID;

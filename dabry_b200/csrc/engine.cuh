@@ -42,6 +42,14 @@ DABRY_HD void counter_add(unsigned long long* c, unsigned long long v) {
 #endif
 }
 
+DABRY_HD void counter_max(unsigned long long* c, unsigned long long v) {
+#if defined(__CUDA_ARCH__)
+    atomicMax(c, v);
+#else
+    if (v > *c) *c = v;
+#endif
+}
+
 // ---- phases -----------------------------------------------------------------------------------------------
 
 struct FillI32Phase {
@@ -291,6 +299,8 @@ struct PackGridPhase {
     double* out;           // pair records
     int32_t nt, nx, ny;
     double two_dx, two_dy;
+    double scaler_speed;             // WrapperFF._scaler_speed
+    unsigned long long* max_norm;    // bits of max |scaler * w| over the nodes (non-negative doubles order like integers)
     DABRY_HD void node(int k, int ix, int iy, double* c) const {
         const int64_t n = ((int64_t) k * nx + ix) * ny + iy;
         c[0] = values[2 * n];
@@ -324,6 +334,14 @@ struct PackGridPhase {
         for (int c = 0; c < 6; ++c) {
             o[2 * c] = a[c];
             o[2 * c + 1] = b[c];
+        }
+        if (k >= 0) {
+            // np.max(np.linalg.norm(scaler * values, axis=-1)) (solver_ef.py:459, flowfield.py:547-548), same roundings
+            const double su = mul_rn(scaler_speed, a[0]), sv = mul_rn(scaler_speed, a[1]);
+            const double norm = sqrt(add_rn(mul_rn(su, su), mul_rn(sv, sv)));
+            unsigned long long key;
+            memcpy(&key, &norm, sizeof(key));
+            if (norm == norm && key > *max_norm) counter_max(max_norm, key);
         }
     }
 };
@@ -397,6 +415,8 @@ struct GatherRecordPhase {
         r.parent_next = S.parent_next[s];
         r.n_target_events = S.n_target_events[s];
         r.ivp_status = S.ivp_status[s];
+        r.flags = S.flags[s];
+        r.pad_ = 0;
         r.t_enter_obs = S.t_enter_obs[s];
         r.cost0 = S.cost0[s];
         for (int e = 0; e < DABRY_MAX_TARGET_EVENTS; ++e)
@@ -542,8 +562,16 @@ public:
             G.spacing[a] = (a == 0 && !unsteady) ? 1. : (hi[a] - lo[a]) / (double) (n_ax[a] - 1);
             G.inv_spacing[a] = 1. / G.spacing[a];
         }
-        PackGridPhase ph{d_values, d_grad, d_grid, nt, nx, ny, 2 * G.spacing[1], 2 * G.spacing[2]};
+        unsigned long long* d_key = (unsigned long long*) be.alloc(sizeof(unsigned long long));
+        be.zero(d_key, sizeof(unsigned long long));
+        PackGridPhase ph{d_values, d_grad, d_grid, nt, nx, ny, 2 * G.spacing[1], 2 * G.spacing[2],
+                         w ? w->scaler_speed : 1., d_key};
         be.launch(records, ph);
+        unsigned long long key = 0;
+        be.download(&key, d_key, sizeof(key));
+        be.free(d_key);
+        memcpy(&flow_max_norm, &key, sizeof(key));
+        if (cfg.ff_max_norm < 0.) C.ff_max_norm = flow_max_norm;  // "auto": the device-computed value
         be.sync();
         be.free(d_values);
         be.free(d_grad);
@@ -801,13 +829,14 @@ public:
         stats.ivp_calls = c.ivp_calls;
         stats.rhs_evals = cfg.integrator == DABRY_RK4_FIXED ? 4 * c.rk_steps : 6 * c.rk_steps + 2 * c.ivp_calls;
         stats.kernel_launches = be.launches();
-        stats.n_sites = n_sites - has_ghost;
+        stats.n_sites = n_sites;  // device slots, including the ghost slot of a sharded ring (record flag bit 0)
         stats.capacity = S.capacity;
         *out = stats;
         return check();
     }
 
     int64_t num_sites() const { return n_sites; }
+    double flow_max_norm = 0.;  // max |w| over the grid nodes (0 for analytic fields)
     int64_t solution() const { return solution_site; }
     double solution_cost_value() const { return solution_cost; }
 

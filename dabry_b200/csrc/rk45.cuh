@@ -12,6 +12,22 @@ namespace dabry {
 #define DABRY_RK_MIN_FACTOR 0.2
 #define DABRY_RK_MAX_FACTOR 10.0
 
+// Dormand-Prince 5(4) coefficients (rk.py:538-565).  On the device they live in constant memory so that an FMA reads
+// its coefficient straight from the constant bank instead of materialising a 64-bit immediate in two moves.
+struct DormandPrince {
+    double a21, a31, a32, a41, a42, a43, a51, a52, a53, a54, a61, a62, a63, a64, a65, b1, b3, b4, b5, b6, c2, c3, c4, c5, e1, e3, e4, e5, e6, e7, p11, p13, p14, p15, p16, p17, p21, p23, p24, p25, p26, p27, p31, p33, p34, p35, p36, p37;
+};
+#define DABRY_DP_INIT {1. / 5., 3. / 40., 9. / 40., 44. / 45., -56. / 15., 32. / 9., 19372. / 6561., -25360. / 2187., 64448. / 6561., -212. / 729., 9017. / 3168., -355. / 33., 46732. / 5247., 49. / 176., -5103. / 18656., 35. / 384., 500. / 1113., 125. / 192., -2187. / 6784., 11. / 84., 1. / 5., 3. / 10., 4. / 5., 8. / 9., -71. / 57600., 71. / 16695., -71. / 1920., 17253. / 339200., -22. / 525., 1. / 40., -8048581381. / 2820520608., 131558114200. / 32700410799., -1754552775. / 470086768., 127303824393. / 49829197408., -282668133. / 205662961., 40617522. / 29380423., 8663915743. / 2820520608., -68118460800. / 10900136933., 14199869525. / 1410260304., -318862633887. / 49829197408., 2019193451. / 616988883., -110615467. / 29380423., -12715105075. / 11282082432., 87487479700. / 32700410799., -10690763975. / 1880347072., 701980252875. / 199316789632., -1453857185. / 822651844., 69997945. / 29380423.}
+#if defined(__CUDACC__)
+__constant__ DormandPrince c_dp = DABRY_DP_INIT;
+#endif
+static const DormandPrince h_dp = DABRY_DP_INIT;
+#if defined(__CUDA_ARCH__)
+#define DP(x) (c_dp.x)
+#else
+#define DP(x) (h_dp.x)
+#endif
+
 template <int N>
 struct RkState {
     double t, t_old, h_abs;
@@ -89,36 +105,36 @@ DABRY_HD bool rk_step(RkState<N>& S, const Rhs& rhs, double t_bound, double max_
         // Dormand-Prince stages (rk.py:538-552)
         double ys[N];
 #pragma unroll
-        for (int i = 0; i < N; ++i) ys[i] = S.y[i] + (1. / 5. * S.K[0][i]) * h;
-        rhs(t + 1. / 5. * h, ys, S.K[1]);
+        for (int i = 0; i < N; ++i) ys[i] = S.y[i] + (DP(a21) * S.K[0][i]) * h;
+        rhs(t + DP(c2) * h, ys, S.K[1]);
 #pragma unroll
-        for (int i = 0; i < N; ++i) ys[i] = S.y[i] + (3. / 40. * S.K[0][i] + 9. / 40. * S.K[1][i]) * h;
-        rhs(t + 3. / 10. * h, ys, S.K[2]);
-#pragma unroll
-        for (int i = 0; i < N; ++i)
-            ys[i] = S.y[i] + (44. / 45. * S.K[0][i] - 56. / 15. * S.K[1][i] + 32. / 9. * S.K[2][i]) * h;
-        rhs(t + 4. / 5. * h, ys, S.K[3]);
+        for (int i = 0; i < N; ++i) ys[i] = S.y[i] + (DP(a31) * S.K[0][i] + DP(a32) * S.K[1][i]) * h;
+        rhs(t + DP(c3) * h, ys, S.K[2]);
 #pragma unroll
         for (int i = 0; i < N; ++i)
-            ys[i] = S.y[i] + (19372. / 6561. * S.K[0][i] - 25360. / 2187. * S.K[1][i] + 64448. / 6561. * S.K[2][i]
-                              - 212. / 729. * S.K[3][i]) * h;
-        rhs(t + 8. / 9. * h, ys, S.K[4]);
+            ys[i] = S.y[i] + (DP(a41) * S.K[0][i] + DP(a42) * S.K[1][i] + DP(a43) * S.K[2][i]) * h;
+        rhs(t + DP(c4) * h, ys, S.K[3]);
 #pragma unroll
         for (int i = 0; i < N; ++i)
-            ys[i] = S.y[i] + (9017. / 3168. * S.K[0][i] - 355. / 33. * S.K[1][i] + 46732. / 5247. * S.K[2][i]
-                              + 49. / 176. * S.K[3][i] - 5103. / 18656. * S.K[4][i]) * h;
+            ys[i] = S.y[i] + (DP(a51) * S.K[0][i] + DP(a52) * S.K[1][i] + DP(a53) * S.K[2][i]
+                              + DP(a54) * S.K[3][i]) * h;
+        rhs(t + DP(c5) * h, ys, S.K[4]);
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            ys[i] = S.y[i] + (DP(a61) * S.K[0][i] + DP(a62) * S.K[1][i] + DP(a63) * S.K[2][i]
+                              + DP(a64) * S.K[3][i] + DP(a65) * S.K[4][i]) * h;
         rhs(t + h, ys, S.K[5]);
 #pragma unroll
         for (int i = 0; i < N; ++i)
-            y_new[i] = S.y[i] + h * (35. / 384. * S.K[0][i] + 500. / 1113. * S.K[2][i] + 125. / 192. * S.K[3][i]
-                                     - 2187. / 6784. * S.K[4][i] + 11. / 84. * S.K[5][i]);
+            y_new[i] = S.y[i] + h * (DP(b1) * S.K[0][i] + DP(b3) * S.K[2][i] + DP(b4) * S.K[3][i]
+                                     + DP(b5) * S.K[4][i] + DP(b6) * S.K[5][i]);
         rhs(t + h, y_new, S.K[6]);
         // error estimate (rk.py:105-109, :146-147)
         double err[N], scale[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            err[i] = (-71. / 57600. * S.K[0][i] + 71. / 16695. * S.K[2][i] - 71. / 1920. * S.K[3][i]
-                      + 17253. / 339200. * S.K[4][i] - 22. / 525. * S.K[5][i] + 1. / 40. * S.K[6][i]) * h;
+            err[i] = (DP(e1) * S.K[0][i] + DP(e3) * S.K[2][i] + DP(e4) * S.K[3][i]
+                      + DP(e5) * S.K[4][i] + DP(e6) * S.K[5][i] + DP(e7) * S.K[6][i]) * h;
             scale[i] = atol + dmax(fabs(S.y[i]), fabs(y_new[i])) * rtol;
         }
         const double error_norm = rms_norm_scaled<N>(err, scale);
@@ -173,15 +189,9 @@ DABRY_HD void rk_dense(const RkState<N>& S, Dense<N>& D) {
         D.y_old[i] = S.y_old[i];
         const double k0 = S.K[0][i], k2 = S.K[2][i], k3 = S.K[3][i], k4 = S.K[4][i], k5 = S.K[5][i], k6 = S.K[6][i];
         D.Q[i][0] = k0;
-        D.Q[i][1] = -8048581381. / 2820520608. * k0 + 131558114200. / 32700410799. * k2
-                    - 1754552775. / 470086768. * k3 + 127303824393. / 49829197408. * k4
-                    - 282668133. / 205662961. * k5 + 40617522. / 29380423. * k6;
-        D.Q[i][2] = 8663915743. / 2820520608. * k0 - 68118460800. / 10900136933. * k2
-                    + 14199869525. / 1410260304. * k3 - 318862633887. / 49829197408. * k4
-                    + 2019193451. / 616988883. * k5 - 110615467. / 29380423. * k6;
-        D.Q[i][3] = -12715105075. / 11282082432. * k0 + 87487479700. / 32700410799. * k2
-                    - 10690763975. / 1880347072. * k3 + 701980252875. / 199316789632. * k4
-                    - 1453857185. / 822651844. * k5 + 69997945. / 29380423. * k6;
+        D.Q[i][1] = DP(p11) * k0 + DP(p13) * k2 + DP(p14) * k3 + DP(p15) * k4 + DP(p16) * k5 + DP(p17) * k6;
+        D.Q[i][2] = DP(p21) * k0 + DP(p23) * k2 + DP(p24) * k3 + DP(p25) * k4 + DP(p26) * k5 + DP(p27) * k6;
+        D.Q[i][3] = DP(p31) * k0 + DP(p33) * k2 + DP(p34) * k3 + DP(p35) * k4 + DP(p36) * k5 + DP(p37) * k6;
     }
 }
 

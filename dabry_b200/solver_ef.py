@@ -142,13 +142,26 @@ class Site:
         self._target_events = np.array(rec['t_target_events'][:n_ev], dtype=float)
         self._traj = None
         self._next_nb = None
-        self.traj_full: Optional[Trajectory] = None
+        self._traj_full: Optional[Trajectory] = None
 
     @property
     def traj(self) -> Trajectory:
         if self._traj is None:
             self._traj = self._solver._fetch_traj(self)
         return self._traj
+
+    @property
+    def traj_full(self) -> Optional[Trajectory]:
+        """Trajectory extended back to t_init through the ancestors (solver_ef.py:701-749).  The reference builds it
+        for every solution site at the end of solve(); here it is built on first access (a 10^6 fan has 10^4+
+        solution sites), and stays None for the other sites like in the reference."""
+        if self._traj_full is None and self._solver._is_solution_slot(self.slot):
+            self._solver.extrapolate_back_traj(self)
+        return self._traj_full
+
+    @traj_full.setter
+    def traj_full(self, value):
+        self._traj_full = value
 
     @property
     def next_nb(self):
@@ -441,10 +454,12 @@ class SolverEFResampling(SolverEF):
         self._max_dist_sq = self.max_dist ** 2
         self.mode_origin = mode_origin
         self.site_mngr = SiteManager(self.n_costate_sectors, self.max_depth)
-        ff = self.pb.model.ff
-        self._ff_max_norm = np.max(np.linalg.norm(ff.values, axis=-1)) if hasattr(ff, 'values') else None
-        self.solution_sites: set = set()
+        # max |w| over the grid nodes (solver_ef.py:459-460): computed by the device while it repacks the grid
+        self._flow_is_grid = isinstance(low.unwrap_flow(self.pb.model.ff)[1], low.DiscreteFF)
+        self._solution_sites: Optional[set] = None
+        self._solution_slots = np.zeros(0, dtype=np.int64)
         self.solution_site: Optional[Site] = None
+        self._n_sites_cache = None
         self._sites: Optional[dict] = None
         self._records = None
         self._slot_cache = {}
@@ -453,7 +468,7 @@ class SolverEFResampling(SolverEF):
     def _default_config(self):
         return self._native_config(self.n_costate_sectors, self.max_depth, max_dist=self.max_dist,
                                    mode_origin=self.mode_origin,
-                                   ff_max_norm=0. if self._ff_max_norm is None else float(self._ff_max_norm),
+                                   ff_max_norm=-1. if self._flow_is_grid else 0.,
                                    n_index_per_subframe=getattr(self, 'n_index_per_subframe', 10),
                                    trimming_band_width=getattr(self, '_trimming_band_width', 3))
 
@@ -466,6 +481,24 @@ class SolverEFResampling(SolverEF):
         offset, count = (0, n) if self.root_range is None else self.root_range
         theta = np.linspace(0, 2 * np.pi, n, endpoint=False)[offset:offset + count]
         return nat.f64(1000 * np.stack((np.cos(theta), np.sin(theta)), -1))
+
+    @property
+    def _ff_max_norm(self):
+        return self._ensure_handle().flow_max_norm() if self._flow_is_grid else None
+
+    @property
+    def solution_sites(self) -> set:
+        if self._solution_sites is None:
+            self._solution_sites = {self._site_by_slot(int(s)) for s in self._solution_slots}
+        return self._solution_sites
+
+    @solution_sites.setter
+    def solution_sites(self, value):
+        self._solution_sites = value
+
+    def _is_solution_slot(self, slot):
+        i = np.searchsorted(self._solution_slots, slot)
+        return i < len(self._solution_slots) and self._solution_slots[i] == slot
 
     # ---- reference API ---------------------------------------------------------------------------------------
     def setup(self):
@@ -488,8 +521,8 @@ class SolverEFResampling(SolverEF):
         self._invalidate()
         self.depth = self.max_depth
         self.check_solutions(_finished=True)
-        for site in self.solution_sites:
-            self.extrapolate_back_traj(site)
+        if self.solution_site is not None:
+            self.extrapolate_back_traj(self.solution_site)  # the other solution sites: on first access of traj_full
 
     def check_solutions(self, _finished=False):
         """Sites with a grid sample strictly inside the target disc; the cheapest is `solution_site`, those within
@@ -501,13 +534,13 @@ class SolverEFResampling(SolverEF):
         index, cost = handle.arrivals(0, n)
         self._arrival_index, self._arrival_cost = index, cost
         slot, best = handle.solution()
-        self.solution_sites = set()
+        self._solution_sites = None
+        self._solution_slots = np.zeros(0, dtype=np.int64)
         self.solution_site = None
         if slot >= 0:
             self.success = True
+            self._solution_slots = np.nonzero((index >= 0) & ~(cost > 1.15 * best))[0]
             self.solution_site = self._site_by_slot(slot)
-            for s in np.nonzero((index >= 0) & ~(cost > 1.15 * best))[0]:
-                self.solution_sites.add(self._site_by_slot(int(s)))
 
     @property
     def solution_cost(self):
@@ -519,7 +552,10 @@ class SolverEFResampling(SolverEF):
         if self._sites is None:
             n = self._n_sites()
             self._sites = {}
+            records = self._all_records()
             for slot in range(n):
+                if records['flags'][slot] & 1:
+                    continue  # ghost copy of the next rank's first root (sharded ring)
                 site = self._site_by_slot(slot)
                 self._sites[site.name] = site
         return self._sites
@@ -579,8 +615,8 @@ class SolverEFResampling(SolverEF):
                 w_next = w_next / 2
                 w_prev = 1 - w_next
             del m
-        site.traj_full = Trajectory(times, states, site.traj.coords, controls=controls, costates=costates,
-                                    cost=cost, events=site.traj.events)
+        site._traj_full = Trajectory(times, states, site.traj.coords, controls=controls, costates=costates,
+                                     cost=cost, events=site.traj.events)
 
     def save_results(self):
         super().save_results()
@@ -597,13 +633,16 @@ class SolverEFResampling(SolverEF):
 
     # ---- device -> host --------------------------------------------------------------------------------------
     def _invalidate(self):
+        self._n_sites_cache = None
         self._sites = None
         self._records = None
         self._slot_cache = {}
         self._bulk = None
 
     def _n_sites(self):
-        return int(self._handle.stats()['n_sites'])
+        if self._n_sites_cache is None:
+            self._n_sites_cache = int(self._handle.stats()['n_sites'])
+        return self._n_sites_cache
 
     def _all_records(self):
         if self._records is None:
@@ -613,7 +652,8 @@ class SolverEFResampling(SolverEF):
     def _site_by_slot(self, slot: int) -> Site:
         site = self._slot_cache.get(slot)
         if site is None:
-            rec = self._all_records()[slot]
+            # one record for a single site of a big front, the whole table once `sites` has been asked for
+            rec = self._records[slot] if self._records is not None else self._handle.sites(slot, 1)[0]
             site = Site(self, slot, rec, self.site_mngr.name_from_index(int(rec['dyadic'])))
             self._slot_cache[slot] = site
         return site

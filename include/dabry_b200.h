@@ -64,7 +64,8 @@ typedef struct dabry_config {
     double target_radius;
     double max_dist;              /* resampling threshold (solver_ef.py:451) */
     double bl[2], tr[2];          /* problem box: cost-map extent (solver_ef.py:825-829) */
-    double ff_max_norm;           /* max |w| over the grid nodes; <= 0 disables trim_distance (solver_ef.py:459, 594-600) */
+    double ff_max_norm;           /* max |w| over the grid nodes (solver_ef.py:459); 0 disables trim_distance (594-600);
+                                     < 0: use the value dabry_set_flow_grid computes on the device */
     const double* times;          /* [n_time] solver.times = linspace(t_init, t_init + T, n_time) (solver_ef.py:313) */
 } dabry_config;
 
@@ -130,6 +131,8 @@ typedef struct dabry_site_record {
     int32_t parent_prev, parent_next; /* slots of the parents, -1 for roots */
     int32_t n_target_events;
     int32_t ivp_status;
+    int32_t flags;           /* bit 0: ghost copy of a neighbouring rank's root (multi-GPU), not a site of this rank */
+    int32_t pad_;
     double t_enter_obs;      /* NaN = None */
     double cost0;            /* cost of the first sample */
     double t_target_events[DABRY_MAX_TARGET_EVENTS];
@@ -206,6 +209,8 @@ int dabry_get_solution(dabry_solver* h, int64_t* site, double* cost);
  * and all times when full != 0 (solver_ef.py:687-688). */
 int dabry_get_cost_map(dabry_solver* h, int32_t full, double* out);
 int dabry_get_stats(dabry_solver* h, dabry_stats* out);
+/* np.max(np.linalg.norm(ff.values, axis=-1)) of the wrapped grid (solver_ef.py:459), computed while repacking. */
+int dabry_get_flow_max_norm(dabry_solver* h, double* out);
 
 /* ---- multi-GPU ring boundary ---------------------------------------------------------------- */
 /* The last root of rank r needs the first root of rank r+1 as its next neighbour (solver_ef.py:468-469).

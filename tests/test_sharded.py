@@ -1,0 +1,71 @@
+"""The multi-GPU path on CPU: two `gloo` ranks, each driving its own handle of tests/hostsim (the device headers
+compiled by g++), shard the ring of root extremals by theta_0 and exchange the ring boundary + the arrival-time
+argmin through torch.distributed exactly like the NCCL run does (dabry_b200/distributed.py).  The union of the two
+shards must reproduce the single-handle result site by site."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import parity_util as pu
+
+WORKER = r'''
+import os, sys, pickle
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, 'tests')); sys.path.insert(0, os.path.join({root!r}, 'oracle'))
+import numpy as np
+import torch.distributed as dist
+import parity_util as pu
+from dabry_b200 import _native
+_native.use_library(pu.HOSTSIM_LIB)
+from dabry_b200.problem import NavigationProblem
+from dabry_b200.solver_ef import SolverEFResampling
+from dabry_b200.distributed import ShardedResampling
+dist.init_process_group('gloo')
+pb = NavigationProblem.from_name({case!r}).rescale()
+runner = ShardedResampling(lambda **kw: SolverEFResampling(pb, max_depth={depth}, n_costate_sectors=30, **kw), 30)
+runner.solve()
+s = runner.solver
+rec = {{'rank': runner.rank, 'names': list(s.sites.keys()), 'cost': runner.global_cost, 'owner': runner.owner_rank,
+       'steps': runner.total_rk_steps, 'local_cost': s.solution_cost,
+       'last': {{n: np.array(site.traj.states[-1]) for n, site in s.sites.items()}},
+       'len': {{n: len(site.traj) for n, site in s.sites.items()}},
+       'closure': {{n: (-1 if site.closure_reason is None else site.closure_reason.value) for n, site in s.sites.items()}}}}
+pickle.dump(rec, open(os.path.join({out!r}, 'rank%d.pkl' % runner.rank), 'wb'))
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize('case,depth', [('linear', 5), ('moving_vortex', 4)])
+def test_two_rank_sharding_matches_single(case, depth, tmp_path, hostsim):
+    import pickle
+    import subprocess
+    script = tmp_path / 'worker.py'
+    script.write_text(WORKER.format(root=pu.ROOT, case=case, depth=depth, out=str(tmp_path)))
+    env = dict(os.environ, MASTER_ADDR='127.0.0.1')
+    subprocess.run([sys.executable, '-W', 'ignore', '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
+                    '--master-addr', '127.0.0.1', '--master-port', '29611', str(script)], check=True, env=env,
+                   timeout=600)
+    recs = [pickle.load(open(tmp_path / ('rank%d.pkl' % r), 'rb')) for r in range(2)]
+
+    from dabry_b200.problem import NavigationProblem
+    from dabry_b200.solver_ef import SolverEFResampling
+    pb = NavigationProblem.from_name(case).rescale()
+    single = SolverEFResampling(pb, max_depth=depth, n_costate_sectors=30)
+    single.solve()
+    # same extremals: the ghost copies are not reported, every site lives on exactly one rank
+    names = recs[0]['names'] + recs[1]['names']
+    assert sorted(names) == sorted(single.sites.keys())
+    assert len(set(names)) == len(names)
+    for rec in recs:
+        for n in rec['names']:
+            site = single.sites[n]
+            assert rec['len'][n] == len(site.traj), n
+            assert rec['closure'][n] == (-1 if site.closure_reason is None else site.closure_reason.value), n
+            assert np.allclose(rec['last'][n], site.traj.states[-1], rtol=1e-12, atol=1e-12), n
+    # arrival-time argmin over ranks == single-handle optimum; both ranks agree on it
+    assert recs[0]['cost'] == recs[1]['cost'] == pytest.approx(single.solution_cost, rel=1e-12)
+    assert recs[0]['owner'] == recs[1]['owner']
+    owner = recs[0]['owner']
+    assert recs[owner]['local_cost'] == recs[0]['cost']
+    assert recs[0]['steps'] == recs[1]['steps'] == single.native_stats()['rk_steps']
