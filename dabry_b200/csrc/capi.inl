@@ -33,8 +33,9 @@ int dabry_create(const dabry_config* c, dabry_solver** out) {
         g_create_error = "dabry_config: need n_time >= 2, times, n_roots >= 1, 0 <= max_depth <= 40, cost map >= 2x2";
         return DABRY_ERR_INVALID;
     }
-    if (c->dtype != DABRY_F64 || c->integrator != DABRY_DOPRI5_SCIPY) {
-        g_create_error = "this build implements dtype F64 with the DOPRI5_SCIPY integrator";
+    if ((c->dtype != DABRY_F64 && c->dtype != DABRY_F32) ||
+        (c->integrator != DABRY_DOPRI5_SCIPY && c->integrator != DABRY_RK4_FIXED)) {
+        g_create_error = "unknown dtype / integrator";
         return DABRY_ERR_UNSUPPORTED;
     }
     dabry::Engine<DABRY_BACKEND>* e = new dabry::Engine<DABRY_BACKEND>(*c);

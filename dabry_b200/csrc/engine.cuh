@@ -118,7 +118,7 @@ struct GhostInitPhase {  // the ghost slot = ring root `ring_index`, evaluated b
     }
 };
 
-template <int FK>
+template <int FK, int METHOD>
 struct FreeArcPhase {  // the hot kernel: one thread per extremal, free arc with events
     static constexpr int kThreads = 128;
     static constexpr int kMinBlocks = DABRY_INTEGRATE_MIN_BLOCKS;  // register cap = 65536 / (128 * kMinBlocks)
@@ -130,14 +130,14 @@ struct FreeArcPhase {  // the hot kernel: one thread per extremal, free arc with
     DABRY_HD void operator()(int64_t i) const {
         const int s = list ? list[i] : base + (int) i;
         unsigned attempts = 0, calls = 0;
-        site_free_arc<FK>(problem(), S, s, index_t, attempts, calls);
+        site_free_arc<FK, METHOD>(problem(), S, s, index_t, attempts, calls);
         counter_add(&counters->rk_steps, attempts);
         counter_add(&counters->ivp_calls, calls);
         captured[i] = (S.arc_from[s] >= 0 && S.obstacle[s] >= 0) ? 0 : -1;
     }
 };
 
-template <int FK>
+template <int FK, int METHOD>
 struct ObstacleArcPhase {  // entry side, feasibility and boundary following for the captured extremals
     static constexpr int kThreads = 128;
     static constexpr int kMinBlocks = 3;
@@ -150,7 +150,7 @@ struct ObstacleArcPhase {  // entry side, feasibility and boundary following for
         const int item = captured[i];
         const int s = list ? list[item] : base + item;
         unsigned attempts = 0, calls = 0;
-        site_obstacle_arcs<FK>(problem(), S, s, index_t, attempts, calls);
+        site_obstacle_arcs<FK, METHOD>(problem(), S, s, index_t, attempts, calls);
         counter_add(&counters->rk_steps, attempts);
         counter_add(&counters->ivp_calls, calls);
     }
@@ -300,6 +300,7 @@ struct PackGridPhase {
     int32_t nt, nx, ny;
     double two_dx, two_dy;
     double scaler_speed;             // WrapperFF._scaler_speed
+    int32_t f32;                     // store the records in fp32 (dtype F32)
     unsigned long long* max_norm;    // bits of max |scaler * w| over the nodes (non-negative doubles order like integers)
     DABRY_HD void node(int k, int ix, int iy, double* c) const {
         const int64_t n = ((int64_t) k * nx + ix) * ny + iy;
@@ -329,11 +330,20 @@ struct PackGridPhase {
         double a[6], b[6];
         node(imax(k, 0), ix, iy, a);
         node(imin(k + 1, nt - 1), ix, iy, b);
-        double* o = out + 12 * i;
+        if (f32) {
+            float* o = reinterpret_cast<float*>(out) + 12 * i;
 #pragma unroll
-        for (int c = 0; c < 6; ++c) {
-            o[2 * c] = a[c];
-            o[2 * c + 1] = b[c];
+            for (int c = 0; c < 6; ++c) {
+                o[2 * c] = (float) a[c];
+                o[2 * c + 1] = (float) b[c];
+            }
+        } else {
+            double* o = out + 12 * i;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                o[2 * c] = a[c];
+                o[2 * c + 1] = b[c];
+            }
         }
         if (k >= 0) {
             // np.max(np.linalg.norm(scaler * values, axis=-1)) (solver_ef.py:459, flowfield.py:547-548), same roundings
@@ -545,7 +555,7 @@ public:
         double* d_values = (double*) be.alloc(sizeof(double) * 2 * nodes);
         double* d_grad = grad ? (double*) be.alloc(sizeof(double) * 4 * nodes) : nullptr;
         be.free(d_grid);
-        d_grid = (double*) be.alloc(sizeof(double) * 12 * records);
+        d_grid = (double*) be.alloc((cfg.dtype == DABRY_F32 ? sizeof(float) : sizeof(double)) * 12 * records);
         if (!d_values || !d_grid || (grad && !d_grad)) return fail(DABRY_ERR_CAPACITY, "flow grid: out of device memory");
         be.upload(d_values, values, sizeof(double) * 2 * nodes);
         if (grad) be.upload(d_grad, grad, sizeof(double) * 4 * nodes);
@@ -564,8 +574,9 @@ public:
         }
         unsigned long long* d_key = (unsigned long long*) be.alloc(sizeof(unsigned long long));
         be.zero(d_key, sizeof(unsigned long long));
+        const int f32 = cfg.dtype == DABRY_F32 ? 1 : 0;
         PackGridPhase ph{d_values, d_grad, d_grid, nt, nx, ny, 2 * G.spacing[1], 2 * G.spacing[2],
-                         w ? w->scaler_speed : 1., d_key};
+                         w ? w->scaler_speed : 1., f32, d_key};
         be.launch(records, ph);
         unsigned long long key = 0;
         be.download(&key, d_key, sizeof(key));
@@ -575,7 +586,7 @@ public:
         be.sync();
         be.free(d_values);
         be.free(d_grad);
-        P.field.kind = FIELD_GRID;
+        P.field.kind = f32 ? FIELD_GRID_F32 : FIELD_GRID;
         set_wrapper(w);
         stats.ms_upload += be.toc();
         return check();
@@ -827,7 +838,7 @@ public:
         be.download(&c, d_counters, sizeof(c));
         stats.rk_steps = c.rk_steps;
         stats.ivp_calls = c.ivp_calls;
-        stats.rhs_evals = cfg.integrator == DABRY_RK4_FIXED ? 4 * c.rk_steps : 6 * c.rk_steps + 2 * c.ivp_calls;
+        stats.rhs_evals = cfg.integrator == DABRY_RK4_FIXED ? 4 * c.rk_steps + c.ivp_calls : 6 * c.rk_steps + 2 * c.ivp_calls;
         stats.kernel_launches = be.launches();
         stats.n_sites = n_sites;  // device slots, including the ghost slot of a sharded ring (record flag bit 0)
         stats.capacity = S.capacity;
@@ -869,6 +880,7 @@ public:
         be.upload(d, t, sizeof(double) * n);
         be.upload(d + n, y, sizeof(double) * 4 * n);
         if (P.field.kind == FIELD_GRID) be.launch(n, EvalRhsPhase<FIELD_GRID>{d, d + n, d + 5 * n});
+        else if (P.field.kind == FIELD_GRID_F32) be.launch(n, EvalRhsPhase<FIELD_GRID_F32>{d, d + n, d + 5 * n});
         else be.launch(n, EvalRhsPhase<FIELD_PROGRAM>{d, d + n, d + 5 * n});
         be.download(dy, d + 5 * n, sizeof(double) * 4 * n);
         return check();
@@ -881,6 +893,7 @@ public:
         be.upload(d, t, sizeof(double) * n);
         be.upload(d + n, x, sizeof(double) * 2 * n);
         if (P.field.kind == FIELD_GRID) be.launch(n, EvalFlowPhase<FIELD_GRID>{d, d + n, d + 3 * n, d + 5 * n});
+        else if (P.field.kind == FIELD_GRID_F32) be.launch(n, EvalFlowPhase<FIELD_GRID_F32>{d, d + n, d + 3 * n, d + 5 * n});
         else be.launch(n, EvalFlowPhase<FIELD_PROGRAM>{d, d + n, d + 3 * n, d + 5 * n});
         be.download(w, d + 3 * n, sizeof(double) * 2 * n);
         be.download(jac, d + 5 * n, sizeof(double) * 4 * n);
@@ -933,6 +946,26 @@ private:
     }
 
     void bind() { be.set_problem(P); }
+
+    template <int V>
+    struct Tag {
+        static constexpr int value = V;
+    };
+    // compile-time (field family, integrator) for the two integrate kernels
+    template <class Fn>
+    void dispatch_field(bool rk4, Fn&& fn) {
+        const int k = P.field.kind;
+        if (k == FIELD_GRID) {
+            if (rk4) fn(Tag<FIELD_GRID>{}, Tag<METHOD_RK4>{});
+            else fn(Tag<FIELD_GRID>{}, Tag<METHOD_DOPRI5>{});
+        } else if (k == FIELD_GRID_F32) {
+            if (rk4) fn(Tag<FIELD_GRID_F32>{}, Tag<METHOD_RK4>{});
+            else fn(Tag<FIELD_GRID_F32>{}, Tag<METHOD_DOPRI5>{});
+        } else {
+            if (rk4) fn(Tag<FIELD_PROGRAM>{}, Tag<METHOD_RK4>{});
+            else fn(Tag<FIELD_PROGRAM>{}, Tag<METHOD_DOPRI5>{});
+        }
+    }
 
     int check() {
         if (!be.ok()) return fail(DABRY_ERR_CUDA, be.error());
@@ -1051,17 +1084,20 @@ private:
     int integrate(const int32_t* list, int32_t base, int64_t n, int index_t) {
         if (int rc = ensure_work(n)) return rc;
         be.tic();
-        if (P.field.kind == FIELD_GRID) be.launch(n, FreeArcPhase<FIELD_GRID>{S, list, base, index_t, d_counters, d_captured});
-        else be.launch(n, FreeArcPhase<FIELD_PROGRAM>{S, list, base, index_t, d_counters, d_captured});
+        const bool rk4 = cfg.integrator == DABRY_RK4_FIXED;
+        dispatch_field(rk4, [&](auto fk, auto method) {
+            be.launch(n, FreeArcPhase<decltype(fk)::value, decltype(method)::value>{S, list, base, index_t, d_counters,
+                                                                                   d_captured});
+        });
         stats.ms_integrate += be.toc();
         if (C.follow_obstacles) {
             be.tic();
             const int64_t n_cap = be.scan_requests(d_captured, n, d_cap_offset, d_cap_list);
             if (n_cap > 0) {
-                if (P.field.kind == FIELD_GRID)
-                    be.launch(n_cap, ObstacleArcPhase<FIELD_GRID>{S, list, d_cap_list, base, index_t, d_counters});
-                else
-                    be.launch(n_cap, ObstacleArcPhase<FIELD_PROGRAM>{S, list, d_cap_list, base, index_t, d_counters});
+                dispatch_field(rk4, [&](auto fk, auto method) {
+                    be.launch(n_cap, ObstacleArcPhase<decltype(fk)::value, decltype(method)::value>{
+                                         S, list, d_cap_list, base, index_t, d_counters});
+                });
             }
             stats.ms_obstacle += be.toc();
         }

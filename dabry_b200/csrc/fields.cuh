@@ -18,7 +18,8 @@
 
 namespace dabry {
 
-enum FieldKind : int32_t { FIELD_PROGRAM = 0, FIELD_GRID = 1 };
+// FIELD_GRID_F32: the same pair records stored in fp32 (48 B per node, three 16-byte loads); arithmetic stays fp64
+enum FieldKind : int32_t { FIELD_PROGRAM = 0, FIELD_GRID = 1, FIELD_GRID_F32 = 2 };
 
 enum LeafKind : int32_t {
     LEAF_UNIFORM = 0,       // p: value(2)                                    flowfield.py:601-620
@@ -255,6 +256,18 @@ DABRY_HD D2 load_pair(const double* p) {
 #endif
 }
 
+struct F4 {
+    double x, y, z, w;
+};
+DABRY_HD F4 load_quad(const float* p) {
+#if defined(__CUDA_ARCH__)
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    return F4{(double) v.x, (double) v.y, (double) v.z, (double) v.w};
+#else
+    return F4{(double) p[0], (double) p[1], (double) p[2], (double) p[3]};
+#endif
+}
+
 // Utils.interpolate (misc.py:570-589) on values and grad_values at once.  Weights come from the UNCLIPPED
 // floor; indices lo and lo + 1 are clipped independently to [0, n - 1]; no wrap in longitude.
 //
@@ -262,6 +275,7 @@ DABRY_HD D2 load_pair(const double* p) {
 // clipped pair (lo, hi) of ANY time position is one record and the time lerp needs no select: k < 0 -> both frame 0,
 // k >= nt - 1 -> both frame nt - 1.  Positions use the host-computed reciprocal spacing (one rounding away from the
 // reference's division; continuous in the result).
+template <bool F32>
 DABRY_HD void grid_eval(const GridDesc& G, double t, double x0, double x1, Flow& o) {
     double wt_lo = 1., wt_hi = 0.;
     int frame = 1;
@@ -283,20 +297,39 @@ DABRY_HD void grid_eval(const GridDesc& G, double t, double x0, double x1, Flow&
     // record indices fit 32 bits (checked at upload); one 64-bit multiply per node for the byte offset
     const unsigned row0 = ((unsigned) frame * (unsigned) G.nx + (unsigned) i0) * (unsigned) G.ny;
     const unsigned row1 = ((unsigned) frame * (unsigned) G.nx + (unsigned) i1) * (unsigned) G.ny;
-    const double* n00 = G.data + (size_t) (row0 + j0) * 12;
-    const double* n01 = G.data + (size_t) (row0 + j1) * 12;
-    const double* n10 = G.data + (size_t) (row1 + j0) * 12;
-    const double* n11 = G.data + (size_t) (row1 + j1) * 12;
-    // corner weights (w_t * w_x) * w_y in the reference; here the time factor is applied per node first
+    // corner weights (w_t * w_x) * w_y in the reference; here the time factor is applied per node last
     const double w00 = wx_lo * wy_lo, w01 = wx_lo * wy_hi, w10 = wx_hi * wy_lo, w11 = wx_hi * wy_hi;
     double acc[6];
+    if (F32) {
+        const float* base = reinterpret_cast<const float*>(G.data);
+        const float* n00 = base + (size_t) (row0 + j0) * 12;
+        const float* n01 = base + (size_t) (row0 + j1) * 12;
+        const float* n10 = base + (size_t) (row1 + j0) * 12;
+        const float* n11 = base + (size_t) (row1 + j1) * 12;
 #pragma unroll
-    for (int c = 0; c < 6; ++c) {
-        const D2 a = load_pair(n00 + 2 * c), b = load_pair(n01 + 2 * c);
-        const D2 d = load_pair(n10 + 2 * c), e = load_pair(n11 + 2 * c);
-        const double lo = ((w00 * a.x + w01 * b.x) + w10 * d.x) + w11 * e.x;
-        const double hi = ((w00 * a.y + w01 * b.y) + w10 * d.y) + w11 * e.y;
-        acc[c] = wt_lo * lo + wt_hi * hi;
+        for (int c = 0; c < 3; ++c) {  // one float4 = two components x (frame k, frame k + 1)
+            const F4 a = load_quad(n00 + 4 * c), b = load_quad(n01 + 4 * c);
+            const F4 d = load_quad(n10 + 4 * c), e = load_quad(n11 + 4 * c);
+            const double lo0 = ((w00 * a.x + w01 * b.x) + w10 * d.x) + w11 * e.x;
+            const double hi0 = ((w00 * a.y + w01 * b.y) + w10 * d.y) + w11 * e.y;
+            const double lo1 = ((w00 * a.z + w01 * b.z) + w10 * d.z) + w11 * e.z;
+            const double hi1 = ((w00 * a.w + w01 * b.w) + w10 * d.w) + w11 * e.w;
+            acc[2 * c] = wt_lo * lo0 + wt_hi * hi0;
+            acc[2 * c + 1] = wt_lo * lo1 + wt_hi * hi1;
+        }
+    } else {
+        const double* n00 = G.data + (size_t) (row0 + j0) * 12;
+        const double* n01 = G.data + (size_t) (row0 + j1) * 12;
+        const double* n10 = G.data + (size_t) (row1 + j0) * 12;
+        const double* n11 = G.data + (size_t) (row1 + j1) * 12;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            const D2 a = load_pair(n00 + 2 * c), b = load_pair(n01 + 2 * c);
+            const D2 d = load_pair(n10 + 2 * c), e = load_pair(n11 + 2 * c);
+            const double lo = ((w00 * a.x + w01 * b.x) + w10 * d.x) + w11 * e.x;
+            const double hi = ((w00 * a.y + w01 * b.y) + w10 * d.y) + w11 * e.y;
+            acc[c] = wt_lo * lo + wt_hi * hi;
+        }
     }
     o.w0 = acc[0];
     o.w1 = acc[1];
@@ -313,7 +346,9 @@ DABRY_HD void field_eval(const FieldDesc& F, double t, double x0, double x1, Flo
     const double xx0 = F.wbl[0] + x0 * F.scale_length;
     const double xx1 = F.wbl[1] + x1 * F.scale_length;
     if (FK == FIELD_GRID) {
-        grid_eval(F.grid, tt, xx0, xx1, o);
+        grid_eval<false>(F.grid, tt, xx0, xx1, o);
+    } else if (FK == FIELD_GRID_F32) {
+        grid_eval<true>(F.grid, tt, xx0, xx1, o);
     } else {
         Flow acc = {0., 0., 0., 0., 0., 0.};
         for (int l = 0; l < F.n_leaves; ++l) {

@@ -47,12 +47,13 @@ struct IvpResult {
 // Events concept:  int count() const;  bool terminal(int e) const;  double value(int e, double t, const double* y) const;
 //                  void record(int e, double t_root);
 // Sink concept:    void emit(int j, double t, const double* y);     j indexes the un-sliced linspace
-template <int N, class Rhs, class Events, class Sink>
+template <int N, int METHOD, class Rhs, class Events, class Sink>
 DABRY_HD void solve_ivp(const Rhs& rhs, Events& events, Sink& sink, double t0, double tf, const double* y0,
                         const EvalGrid& grid, double max_step, double rtol, double atol, IvpResult<N>& res,
                         unsigned& n_attempts) {
     RkState<N> S;
-    rk_init<N>(S, rhs, t0, y0, tf, max_step, rtol, atol);
+    if (METHOD == METHOD_RK4) rk4_init<N>(S, rhs, t0, y0, max_step);
+    else rk_init<N>(S, rhs, t0, y0, tf, max_step, rtol, atol);
     const int ne = events.count();
     double g[DABRY_MAX_EVENTS];
     for (int e = 0; e < ne; ++e) g[e] = events.value(e, t0, y0);
@@ -68,7 +69,9 @@ DABRY_HD void solve_ivp(const Rhs& rhs, Events& events, Sink& sink, double t0, d
             S.t_old = S.t;
             finished = true;
         } else {
-            if (!rk_step<N>(S, rhs, tf, max_step, rtol, atol, n_attempts)) {
+            const bool ok = METHOD == METHOD_RK4 ? rk4_step<N>(S, rhs, tf, max_step, n_attempts)
+                                                 : rk_step<N>(S, rhs, tf, max_step, rtol, atol, n_attempts);
+            if (!ok) {
                 res.status = IVP_FAILED;
                 return;
             }
@@ -89,7 +92,8 @@ DABRY_HD void solve_ivp(const Rhs& rhs, Events& events, Sink& sink, double t0, d
         const bool sample_due = eval_i < grid.n && grid.at(eval_i) <= t;
         if (na == 0 && !sample_due) continue;
         Dense<N> D;
-        rk_dense<N>(S, D);
+        if (METHOD == METHOD_RK4) rk4_dense<N>(S, D);
+        else rk_dense<N>(S, D);
         if (na > 0) {
             // rare path: a copy of the interpolant goes to local memory for the root finder, D itself does not
             const Dense<N> Dev = D;

@@ -204,6 +204,73 @@ DABRY_HD void dense_eval(const Dense<N>& D, double t, double* y) {
         y[i] = D.h * (((D.Q[i][0] * x + D.Q[i][1] * x2) + D.Q[i][2] * x3) + D.Q[i][3] * x4) + D.y_old[i];
 }
 
+// ---- classic fixed-step RK4 (integrator RK4_FIXED) ---------------------------------------------------------------
+// No reference counterpart (the reference only ever runs scipy's RK45): steps of exactly max_step (the last one clipped
+// to t_bound), 4 right-hand sides per step (f(t_new, y_new) is kept as the next step's k1), cubic Hermite local
+// interpolant for the time-grid samples and the event roots.  oracle/solver_port.py holds the same stepper as a
+// scipy OdeSolver subclass, so the driver semantics (events, t_eval) are scipy's in both.
+enum Integrator : int32_t { METHOD_DOPRI5 = 0, METHOD_RK4 = 1 };
+
+template <int N, class Rhs>
+DABRY_HD void rk4_init(RkState<N>& S, const Rhs& rhs, double t0, const double* y0, double max_step) {
+    S.t = t0;
+    S.t_old = t0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) S.y[i] = S.y_old[i] = y0[i];
+    rhs(t0, S.y, S.f);
+    S.h_abs = max_step;
+}
+
+template <int N, class Rhs>
+DABRY_HD bool rk4_step(RkState<N>& S, const Rhs& rhs, double t_bound, double max_step, unsigned& n_attempts) {
+    const double t = S.t;
+    double t_new = t + max_step;
+    if (t_new - t_bound > 0.) t_new = t_bound;
+    const double h = t_new - t;
+    ++n_attempts;
+    double ys[N], k2[N], k3[N], k4[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        S.K[0][i] = S.f[i];
+        ys[i] = S.y[i] + (0.5 * h) * S.K[0][i];
+    }
+    rhs(t + 0.5 * h, ys, k2);
+#pragma unroll
+    for (int i = 0; i < N; ++i) ys[i] = S.y[i] + (0.5 * h) * k2[i];
+    rhs(t + 0.5 * h, ys, k3);
+#pragma unroll
+    for (int i = 0; i < N; ++i) ys[i] = S.y[i] + h * k3[i];
+    rhs(t_new, ys, k4);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        S.y_old[i] = S.y[i];
+        S.y[i] = S.y[i] + (h / 6.) * (((S.K[0][i] + 2. * k2[i]) + 2. * k3[i]) + k4[i]);
+    }
+    rhs(t_new, S.y, S.f);
+#pragma unroll
+    for (int i = 0; i < N; ++i) S.K[6][i] = S.f[i];
+    S.t_old = t;
+    S.t = t_new;
+    return true;
+}
+
+// cubic Hermite interpolant in the polynomial form of Dense: y(t_old + x h) = y_old + h (Q0 x + Q1 x^2 + Q2 x^3)
+template <int N>
+DABRY_HD void rk4_dense(const RkState<N>& S, Dense<N>& D) {
+    D.t_old = S.t_old;
+    D.h = S.t - S.t_old;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        D.y_old[i] = S.y_old[i];
+        const double f0 = S.K[0][i], f1 = S.K[6][i];
+        const double slope = (S.y[i] - S.y_old[i]) / D.h;
+        D.Q[i][0] = f0;
+        D.Q[i][1] = (3. * slope - 2. * f0) - f1;
+        D.Q[i][2] = (f0 + f1) - 2. * slope;
+        D.Q[i][3] = 0.;
+    }
+}
+
 // scipy.optimize.brentq as solve_event_equation calls it (ivp.py:52-77): xtol = rtol = 4 eps, maxiter 100.
 // Restated from the published algorithm (scipy/optimize/Zeros/brentq.c, Brent 1973 with inverse quadratic
 // extrapolation); fa = f(xa), fb = f(xb) are evaluated by the routine itself like the C code does.

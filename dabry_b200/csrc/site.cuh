@@ -198,7 +198,7 @@ struct ConstrSink {
 //
 // Part A - the free arc (solver_ef.py:482-504): solve_ivp on the augmented system with the target / obstacle events.
 // A terminal obstacle event leaves the entry record (obstacle, t_enter_obs, index_t_obs, state at entry) for part B.
-template <int FK>
+template <int FK, int METHOD>
 DABRY_HD void site_free_arc(const ProblemDev& P, const SiteStore& S, int s, int index_t, unsigned& n_attempts,
                             unsigned& n_calls) {
     const int idx0 = site_index_t(S, s);
@@ -215,7 +215,7 @@ DABRY_HD void site_free_arc(const ProblemDev& P, const SiteStore& S, int s, int 
     FreeEvents ev{P, S, s};
     FreeSink sink{S, s, idx0};
     IvpResult<4> res;
-    solve_ivp<4>(rhs, ev, sink, grid.at(0), grid.at(n - 1), y0, grid, P.max_step, P.rtol, P.atol, res, n_attempts);
+    solve_ivp<4, METHOD>(rhs, ev, sink, grid.at(0), grid.at(n - 1), y0, grid, P.max_step, P.rtol, P.atol, res, n_attempts);
     ++n_calls;
     S.ivp_status[s] = res.status;
     S.n_samples[s] += res.n_emitted;
@@ -230,7 +230,7 @@ DABRY_HD void site_free_arc(const ProblemDev& P, const SiteStore& S, int s, int 
 
 // Part B - obstacle entry and boundary following (solver_ef.py:506-576) for a site captured during part A of this
 // call, or captured earlier and not yet at index_t.
-template <int FK>
+template <int FK, int METHOD>
 DABRY_HD void site_obstacle_arcs(const ProblemDev& P, const SiteStore& S, int s, int index_t, unsigned& n_attempts,
                                  unsigned& n_calls) {
     const int idx0 = S.arc_from[s];
@@ -273,7 +273,7 @@ DABRY_HD void site_obstacle_arcs(const ProblemDev& P, const SiteStore& S, int s,
                 ConstrSink<FK> csink{P, S, s, idx0 + n_free + 1, obs, trigo};
                 IvpResult<2> r2;
                 const double x0c[2] = {ye.x0, ye.x1};
-                solve_ivp<2>(crhs, nev, csink, t_enter, t_next, x0c, one, P.max_step, P.rtol, P.atol, r2, n_attempts);
+                solve_ivp<2, METHOD>(crhs, nev, csink, t_enter, t_next, x0c, one, P.max_step, P.rtol, P.atol, r2, n_attempts);
                 ++n_calls;
                 tracked = r2.n_emitted > 0;
                 S.n_samples[s] += r2.n_emitted;
@@ -293,7 +293,7 @@ DABRY_HD void site_obstacle_arcs(const ProblemDev& P, const SiteStore& S, int s,
         QuitEvent<FK> qev{P, obs, false};
         ConstrSink<FK> csink{P, S, s, idx0, obs, trigo};
         IvpResult<2> r3;
-        solve_ivp<2>(crhs, qev, csink, grid.at(j0), grid.at(n - 1), x0c, grid, P.max_step, P.rtol, P.atol, r3,
+        solve_ivp<2, METHOD>(crhs, qev, csink, grid.at(j0), grid.at(n - 1), x0c, grid, P.max_step, P.rtol, P.atol, r3,
                      n_attempts);
         ++n_calls;
         S.ivp_status[s] = r3.status;

@@ -66,8 +66,8 @@ class ShardedResampling:
         recv = np.ascontiguousarray(t_recv.cpu().numpy())
         handle.call('dabry_import_boundary', nat.dptr(recv))
 
-    def solve(self):
-        import torch
+    def solve(self, fetch=True):
+        """fetch=False keeps every per-site array on the device (only the 8-byte optimum crosses to the host)."""
         s = self.solver
         handle = s._ensure_handle()
         handle.call('dabry_setup', s._VARIANT, nat.dptr(s._root_costates()))
@@ -78,10 +78,13 @@ class ShardedResampling:
             handle.call('dabry_step_resample')
         s._invalidate()
         s.depth = s.max_depth
-        s.check_solutions()
+        if fetch:
+            s.check_solutions()
+        else:
+            handle.call('dabry_finish')
         stats = handle.stats()
         # arrival-time argmin over ranks, and the step total for the throughput metric
-        cost = s.solution_cost
+        cost = handle.solution()[1]
         local = np.array([np.inf if np.isnan(cost) else cost])
         t = self._tensor(local.copy())
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN, group=self.group)

@@ -234,7 +234,7 @@ class SolverEF(ABC):
                  t_init: Optional[float] = None, n_costate_norm: int = 10, costate_norm_bounds=(0., 1.),
                  target_radius: Optional[float] = None, abs_max_step: Optional[float] = None,
                  rel_max_step: Optional[float] = 0.01, *, device: int = 0, max_sites: int = 0,
-                 root_range: Optional[tuple] = None):
+                 root_range: Optional[tuple] = None, integrator: str = 'dopri5', dtype: str = 'f64'):
         if mode not in self._ALL_MODES:
             raise ValueError('Mode %s is not defined' % mode)
         if mode == 'energy':
@@ -272,7 +272,14 @@ class SolverEF(ABC):
         self.max_int_step = abs_max_step if rel_max_step is None else min(abs_max_step,
                                                                           rel_max_step * self.total_duration)
         self.dyn_augsys = self.dyn_augsys_cartesian if self.pb.coords == Coords.CARTESIAN else self.dyn_augsys_gcs
-        # native side
+        # native side.  integrator: 'dopri5' = scipy's RK45 restated (the reference's integrator), 'rk4' = classic
+        # fixed-step RK4 with h = max_int_step.  dtype: 'f64', or 'f32' = flow grid stored in fp32 (tolerance 1e-4)
+        if integrator not in ('dopri5', 'rk4'):
+            raise ValueError('integrator must be "dopri5" or "rk4"')
+        if dtype not in ('f64', 'f32'):
+            raise ValueError('dtype must be "f64" or "f32"')
+        self.integrator = integrator
+        self.dtype = dtype
         self.device = device
         self.max_sites = max_sites
         self.root_range = root_range
@@ -336,8 +343,8 @@ class SolverEF(ABC):
         cfg.n_time = self.n_time
         cfg.max_depth = max_depth
         cfg.mode_origin = 1 if mode_origin else 0
-        cfg.integrator = 0
-        cfg.dtype = 0
+        cfg.integrator = 1 if self.integrator == 'rk4' else 0
+        cfg.dtype = 1 if self.dtype == 'f32' else 0
         cfg.device = self.device
         cfg.n_index_per_subframe = n_index_per_subframe
         cfg.trimming_band_width = trimming_band_width

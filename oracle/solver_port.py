@@ -33,6 +33,62 @@ WITHIN_OBS, SUBOPTIMAL, IMPOSSIBLE_OBS_TRACKING = 1, 2, 3
 SELF_AND_NB_IN_OBS = 0
 
 
+class _HermiteDense(scitg.DenseOutput):
+    """Cubic Hermite interpolant of one RK4 step, evaluated in the same operation order as the device
+    (csrc/rk45.cuh rk4_dense + dense_eval)."""
+
+    def __init__(self, t_old, t, y_old, y, f_old, f):
+        super().__init__(t_old, t)
+        self.h = t - t_old
+        self.y_old = y_old
+        slope = (y - y_old) / self.h
+        self.q0 = f_old
+        self.q1 = (3. * slope - 2. * f_old) - f
+        self.q2 = (f_old + f) - 2. * slope
+
+    def _call_impl(self, t):
+        x = (np.asarray(t) - self.t_old) / self.h
+        x2 = x * x
+        x3 = x2 * x
+        if x.ndim == 0:
+            return self.h * ((self.q0 * x + self.q1 * x2) + self.q2 * x3) + self.y_old
+        q0, q1, q2, y0 = (a[:, None] for a in (self.q0, self.q1, self.q2, self.y_old))
+        return self.h * ((q0 * x + q1 * x2) + q2 * x3) + y0
+
+
+class RK4Fixed(scitg.OdeSolver):
+    """Integrator RK4_FIXED as a scipy OdeSolver, so that `solve_ivp(method=RK4Fixed)` applies scipy's own driver
+    (events, brentq roots, t_eval sampling) around it: classic RK4 with steps of exactly max_step (the last clipped
+    to t_bound), 4 right-hand sides per step, Hermite dense output.  The reference has no counterpart (it always
+    runs RK45); this defines the semantics of the device's fixed-step variant (csrc/rk45.cuh rk4_step)."""
+
+    def __init__(self, fun, t0, y0, t_bound, max_step=np.inf, vectorized=False, **extraneous):
+        super().__init__(fun, t0, y0, t_bound, vectorized, support_complex=True)
+        self.max_step = max_step
+        self.f = self.fun(self.t, self.y)
+        self.y_old = None
+        self.f_old = None
+
+    def _step_impl(self):
+        t, y = self.t, self.y
+        t_new = t + self.max_step
+        if t_new - self.t_bound > 0:
+            t_new = self.t_bound
+        h = t_new - t
+        k1 = self.f
+        k2 = self.fun(t + 0.5 * h, y + (0.5 * h) * k1)
+        k3 = self.fun(t + 0.5 * h, y + (0.5 * h) * k2)
+        k4 = self.fun(t_new, y + h * k3)
+        y_new = y + (h / 6.) * (((k1 + 2. * k2) + 2. * k3) + k4)
+        self.y_old, self.f_old = y, k1
+        self.t, self.y = t_new, y_new
+        self.f = self.fun(t_new, y_new)
+        return True, None
+
+    def _dense_output_impl(self):
+        return _HermiteDense(self.t_old, self.t, self.y_old, self.y, self.f_old, self.f)
+
+
 def _is_gcs(pb):
     return getattr(pb.coords, 'value', pb.coords) == 'gcs'
 
@@ -92,7 +148,7 @@ class PortSite:
 class Port:
     def __init__(self, pb, total_duration=None, max_depth=20, n_time=100, n_costate_sectors=30, t_init=None,
                  target_radius=None, abs_max_step=None, rel_max_step=0.01, max_dist=None, mode_origin=True,
-                 n_index_per_subframe=10, trimming_band_width=3, root_range=None):
+                 n_index_per_subframe=10, trimming_band_width=3, root_range=None, integrator='dopri5'):
         self.pb = pb
         if total_duration is None:
             total_duration = 1.1 * pb.auto_time_upper_bound()
@@ -114,6 +170,7 @@ class Port:
         self.q = n_index_per_subframe
         self.band = trimming_band_width
         self.root_range = root_range
+        self.integrator = integrator
         self.gcs = _is_gcs(pb)
         # event table (solver_ef.py:322-334)
         self.event_names = ['target']
@@ -188,9 +245,13 @@ class Port:
         return evs
 
     def _ivp(self, *a, **k):
-        res = scitg.solve_ivp(*a, **k)
+        if self.integrator == 'rk4':
+            res = scitg.solve_ivp(*a, method=RK4Fixed, **k)
+            self.n_rk += (res.nfev - 1) // 4
+        else:
+            res = scitg.solve_ivp(*a, **k)
+            self.n_rk += (res.nfev - 2) // 6
         self.n_ivp += 1
-        self.n_rk += (res.nfev - 2) // 6
         return res
 
     # ---- one extremal ---------------------------------------------------------------------------------------
