@@ -1,0 +1,232 @@
+"""Parity of the pieces of the hot path in isolation, and of the two non-reference variants:
+
+* `dabry_eval_rhs` / `dabry_eval_flow` (device A3/A4: augmented RHS, trilinear sampling, WrapperFF scalings, device
+  compute_derivatives) against the numpy restatement of the reference (`pb.augsys_dyn_timeopt_*`, `ff.value/d_value`)
+  at random points including points outside the grid and outside the time window;
+* integrator RK4_FIXED against the oracle's scipy OdeSolver of the same stepper;
+* dtype F32 (flow grid stored in fp32) against the fp64 run, tolerance 1e-4 (BASELINE.json north_star);
+* edge cases: a single root, a fan that never reaches the target, capacity growth, bad arguments.
+
+Every test body runs twice: on the GPU through libdabry_b200.so (`-m gpu`) and on tests/hostsim (CPU tier).
+"""
+import numpy as np
+import pytest
+
+import parity_util as pu
+from dump import solver_record
+
+
+def _both(fn):
+    """Register `fn(...)` as a hostsim test and as a gpu test."""
+    def host(hostsim):
+        fn()
+
+    def gpu(cuda_lib):
+        fn()
+    host.__name__ = fn.__name__ + '_hostsim'
+    gpu.__name__ = fn.__name__ + '_gpu'
+    host.__doc__ = gpu.__doc__ = fn.__doc__
+    return host, pytest.mark.gpu(gpu)
+
+
+def _synthetic(gen, shape, **kw):
+    from dabry_b200 import synthetic
+    from dabry_b200.flowfield import DiscreteFF
+    from dabry_b200.misc import Coords
+    from dabry_b200.obstacle import CircleObs
+    from dabry_b200.penalty import CirclePenalty
+    from dabry_b200.problem import NavigationProblem
+    sc = getattr(synthetic, gen)(*shape)
+    ff = DiscreteFF(sc.values, sc.bounds, Coords.GCS if sc.coords == 'gcs' else Coords.CARTESIAN)
+    obstacles = [CircleObs(np.array(c), float(r)) for c, r in sc.circle_obstacles]
+    penalty = CirclePenalty(np.array(sc.circle_penalty[0]), *map(float, sc.circle_penalty[1:])) \
+        if sc.circle_penalty else None
+    pb = NavigationProblem(ff, sc.x_init, sc.x_target, sc.srf, bl=sc.bl, tr=sc.tr, obstacles=obstacles,
+                           penalty=penalty).rescale()
+    return pb, sc
+
+
+def _random_points(pb, n, seed, margin=0.15):
+    rng = np.random.default_rng(seed)
+    span = pb.tr - pb.bl
+    x = pb.bl - margin * span + rng.uniform(0, 1, (n, 2)) * (1 + 2 * margin) * span
+    theta = rng.uniform(0, 2 * np.pi, n)
+    p = rng.uniform(0.5, 1000., n)[:, None] * np.stack((np.cos(theta), np.sin(theta)), -1)
+    return x, p
+
+
+def rhs_and_flow_parity():
+    """A3 + A4 + A5 + A6 on the device == numpy restatement, planar/spherical, with a penalty, to 1e-12."""
+    from dabry_b200.solver_ef import SolverEFResampling
+    for gen, shape, seed in (('planar_waves', (7, 40, 33), 1), ('era5_like', (6, 60, 31), 2),
+                             ('regional_constrained', (5, 41, 23), 3)):
+        pb, sc = _synthetic(gen, shape)
+        solver = SolverEFResampling(pb, 1.0, n_costate_sectors=4, max_depth=1)
+        x, p = _random_points(pb, 300, seed)
+        t_lo, t_hi = pb.model.ff.t_start, pb.model.ff.t_end
+        t = np.random.default_rng(seed).uniform(t_lo - 0.2 * (t_hi - t_lo), t_hi + 0.2 * (t_hi - t_lo), 300)
+        dy = solver.dyn_augsys_device(t, np.hstack((x, p)))
+        ref = np.array([solver.dyn_augsys(t[i], np.hstack((x[i], p[i]))) for i in range(300)])
+        scale = np.maximum(1., np.abs(ref).max(axis=0))
+        assert np.max(np.abs(dy - ref) / scale) < 1e-12, gen
+        w, jac = solver._ensure_handle().eval_flow(t, x)
+        w_ref = np.array([pb.model.ff.value(t[i], x[i]) for i in range(300)])
+        j_ref = np.array([pb.model.ff.d_value(t[i], x[i]) for i in range(300)])
+        assert np.max(np.abs(w - w_ref)) < 1e-12 * max(1., np.abs(w_ref).max())
+        assert np.max(np.abs(jac - j_ref)) < 1e-12 * max(1., np.abs(j_ref).max())
+        # max |w| over the nodes, computed by the repack kernel == numpy on the wrapped values (solver_ef.py:459)
+        assert solver._ff_max_norm == np.max(np.linalg.norm(pb.model.ff.values, axis=-1))
+        solver.close()
+
+
+def analytic_rhs_parity():
+    """Analytic leaves (A17 and the other catalogue fields) through the expression-tree lowering."""
+    from dabry_b200.problem import NavigationProblem
+    from dabry_b200.solver_ef import SolverEFResampling
+    for name in ('gyre', 'moving_vortex', 'three_vortices', 'trap', 'big_rankine', 'point_symmetric_techy2011',
+                 'chertovskih', 'linear', 'four_vortices', 'three_obstacles'):
+        pb = NavigationProblem.from_name(name).rescale()
+        solver = SolverEFResampling(pb, 1.0, n_costate_sectors=4, max_depth=1)
+        x, p = _random_points(pb, 200, 7)
+        t = np.random.default_rng(5).uniform(-0.1, 1.2, 200)
+        dy = solver.dyn_augsys_device(t, np.hstack((x, p)))
+        ref = np.array([solver.dyn_augsys(t[i], np.hstack((x[i], p[i]))) for i in range(200)])
+        scale = np.maximum(1., np.abs(ref).max(axis=0))
+        assert np.max(np.abs(dy - ref) / scale) < 1e-11, name
+        solver.close()
+
+
+def rk4_fixed_matches_oracle():
+    """Integrator RK4_FIXED == the oracle's scipy OdeSolver with the same stepper (events, obstacles, sphere)."""
+    from dabry_b200.problem import NavigationProblem
+    from dabry_b200.solver_ef import SolverEFResampling
+    from solver_port import Port
+    for name in ('gyre', 'obstacle', 'spherical_geodesic'):
+        pb = NavigationProblem.from_name(name).rescale()
+        kw = dict(max_depth=3, n_costate_sectors=24, n_time=101)
+        solver = SolverEFResampling(pb, integrator='rk4', **kw)
+        solver.solve()
+        port = Port(pb, integrator='rk4', **kw).run_resampling()
+        mine, ref = solver_record(solver, full=True), pu.port_record(port)
+        pu.compare_sites_record(mine, ref)
+        pu.compare_full_trajectories(mine, ref)
+        stats = solver.native_stats()
+        assert stats['rk_steps'] == port.n_rk and stats['ivp_calls'] == port.n_ivp
+        assert stats['rhs_evals'] == 4 * port.n_rk + port.n_ivp
+        solver.close()
+
+
+def f32_grid_within_tolerance():
+    """dtype F32: same extremal counts and arrival cost, endpoints within 1e-4 of the fp64 run."""
+    from cases import CASES, build_problem, solver_args
+    from dabry_b200.solver_ef import SolverEFResampling
+    for key in ('era5_like_R', 'planar_waves_R'):
+        case = CASES[key]
+        pb = build_problem(case, pu.package_api())
+        args, kw = solver_args(case, pb)
+        a = SolverEFResampling(*args, **kw)
+        a.solve()
+        b = SolverEFResampling(*args, dtype='f32', **kw)
+        b.solve()
+        assert list(a.sites.keys()) == list(b.sites.keys())
+        assert a.solution_cost == pytest.approx(b.solution_cost, rel=1e-4)
+        for name, sa in a.sites.items():
+            sb = b.sites[name]
+            assert len(sa.traj) == len(sb.traj) and sa.closure_reason == sb.closure_reason
+            assert np.allclose(sa.traj.states[-1], sb.traj.states[-1], rtol=1e-4, atol=1e-4)
+        a.close()
+        b.close()
+
+
+def edge_cases():
+    from dabry_b200 import _native as nat
+    from dabry_b200.problem import NavigationProblem
+    from dabry_b200.solver_ef import SolverEFResampling
+    pb = NavigationProblem.from_name('linear').rescale()
+    # one root: the ring closes on itself, nothing to resample
+    s = SolverEFResampling(pb, n_costate_sectors=1, max_depth=3)
+    s.solve()
+    assert len(s.sites) == 1 and list(s.sites)[0] == ''.rjust(0, 'A') + s.site_mngr.name_from_index(0)
+    s.close()
+    # a horizon too short to arrive: no solution, NaN cost, success False
+    s = SolverEFResampling(pb, 0.05, max_depth=2)
+    s.solve()
+    assert not s.success and s.solution_site is None and np.isnan(s.solution_cost) and len(s.solution_sites) == 0
+    s.close()
+    # tiny initial capacity: the site store grows on demand and the result does not change
+    big = SolverEFResampling(pb, max_depth=6)
+    big.solve()
+    small = SolverEFResampling(pb, max_depth=6, max_sites=31)
+    small.solve()
+    assert list(big.sites) == list(small.sites)
+    assert small.native_stats()['capacity'] >= len(small.sites)
+    for n in big.sites:
+        assert np.array_equal(big.sites[n].traj.states, small.sites[n].traj.states)
+    big.close()
+    small.close()
+    # argument errors surface as exceptions with the library's message
+    with pytest.raises(ValueError):
+        SolverEFResampling(pb, integrator='euler')
+    bad = SolverEFResampling(pb, max_depth=2, root_range=(20, 40))
+    with pytest.raises(nat.NativeError):
+        bad.setup()
+
+
+test_rhs_and_flow_parity_hostsim, test_rhs_and_flow_parity_gpu = _both(rhs_and_flow_parity)
+test_analytic_rhs_parity_hostsim, test_analytic_rhs_parity_gpu = _both(analytic_rhs_parity)
+test_rk4_fixed_matches_oracle_hostsim, test_rk4_fixed_matches_oracle_gpu = _both(rk4_fixed_matches_oracle)
+test_f32_grid_within_tolerance_hostsim, test_f32_grid_within_tolerance_gpu = _both(f32_grid_within_tolerance)
+test_edge_cases_hostsim, test_edge_cases_gpu = _both(edge_cases)
+
+
+def test_library_exports_every_declared_symbol():
+    """Every function include/dabry_b200.h declares is exported by the built CUDA library and bound by ctypes (no
+    compute call: this runs without a GPU)."""
+    import ctypes
+    import os
+    import re
+    from dabry_b200 import _native as nat
+    header = open(os.path.join(pu.ROOT, 'include', 'dabry_b200.h')).read()
+    declared = set(re.findall(r'\b(dabry_[a-z0-9_]+)\s*\(', header))
+    declared -= {'dabry_solver'}
+    assert declared == set(nat.SIGNATURES), declared ^ set(nat.SIGNATURES)
+    assert os.path.exists(nat.DEFAULT_LIBRARY), 'build the extension: python -c "import __graft_entry__ as g; g.build()"'
+    lib = ctypes.CDLL(nat.DEFAULT_LIBRARY)
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib.dabry_backend_name.restype = ctypes.c_char_p
+    assert lib.dabry_backend_name() == b'cuda-sm100a'
+    assert lib.dabry_abi_version() == nat.ABI_VERSION
+    # ctypes mirrors of the ABI structs have the C sizes (checked against a compiled probe)
+    import subprocess
+    import tempfile
+    probe = ('#include "dabry_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu",'
+             'sizeof(dabry_config),sizeof(dabry_wrapper),sizeof(dabry_leaf),sizeof(dabry_obstacle),'
+             'sizeof(dabry_penalty),sizeof(dabry_site_record),sizeof(dabry_stats));}')
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, 'probe.c')
+        open(src, 'w').write(probe)
+        subprocess.run(['gcc', '-I', os.path.join(pu.ROOT, 'include'), src, '-o', os.path.join(d, 'probe')], check=True)
+        sizes = list(map(int, subprocess.run([os.path.join(d, 'probe')], capture_output=True, text=True).stdout.split()))
+    assert sizes == [ctypes.sizeof(nat.Config), ctypes.sizeof(nat.Wrapper), ctypes.sizeof(nat.Leaf),
+                     ctypes.sizeof(nat.Obstacle), ctypes.sizeof(nat.Penalty), nat.SITE_RECORD_DTYPE.itemsize,
+                     ctypes.sizeof(nat.Stats)]
+
+
+def test_no_cpu_fallback_without_device():
+    """On a machine without a CUDA device the product library refuses to create a solver (no CPU path)."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip('a GPU is present')
+    except ImportError:
+        pass
+    from dabry_b200 import _native as nat
+    from dabry_b200.problem import NavigationProblem
+    from dabry_b200.solver_ef import SolverEFResampling
+    nat.use_library(None)
+    pb = NavigationProblem.from_name('linear').rescale()
+    solver = SolverEFResampling(pb, 1.0, max_depth=1)
+    with pytest.raises(nat.NativeError) as err:
+        solver.solve()
+    assert err.value.code == -2  # DABRY_ERR_NO_DEVICE
