@@ -96,6 +96,10 @@ SIGNATURES = {
     'dabry_step': (C.c_int, [_H]),
     'dabry_step_integrate': (C.c_int, [_H]),
     'dabry_step_resample': (C.c_int, [_H]),
+    'dabry_step_trim_integrate': (C.c_int, [_H]),
+    'dabry_step_trim_refine': (C.c_int, [_H]),
+    'dabry_step_trim_close': (C.c_int, [_H]),
+    'dabry_set_cost_map': (C.c_int, [_H, c_double_p]),
     'dabry_finish': (C.c_int, [_H]),
     'dabry_solve': (C.c_int, [_H, C.c_int32, c_double_p]),
     'dabry_num_sites': (C.c_int, [_H, C.POINTER(C.c_int64)]),

@@ -110,6 +110,27 @@ int dabry_step_resample(dabry_solver* h) {
     return E.step_resample();
 }
 
+int dabry_step_trim_integrate(dabry_solver* h) {
+    DABRY_GUARD(h);
+    return E.step_trim_integrate();
+}
+
+int dabry_step_trim_refine(dabry_solver* h) {
+    DABRY_GUARD(h);
+    return E.step_trim_refine();
+}
+
+int dabry_step_trim_close(dabry_solver* h) {
+    DABRY_GUARD(h);
+    return E.step_trim_close();
+}
+
+int dabry_set_cost_map(dabry_solver* h, const double* map) {
+    DABRY_GUARD(h);
+    if (!map) return DABRY_ERR_INVALID;
+    return E.set_cost_map(map);
+}
+
 int dabry_finish(dabry_solver* h) {
     DABRY_GUARD(h);
     return E.finish();

@@ -662,6 +662,7 @@ public:
         shoot_end = (int32_t) cfg.root_count;
         round = 0;
         i_subframe = 0;
+        trim_stage = 0;
         solution_site = -1;
         solution_cost = NAN;
         arrivals_ready = false;
@@ -710,31 +711,77 @@ public:
     }
 
     // SolverEFTrimming.step (solver_ef.py:802-817)
-    int step_trimming() {
+    // SolverEFTrimming.step (solver_ef.py:802-817) in three parts, so that a sharded run can exchange the ring
+    // boundary after (1) and all_reduce(MIN) the cost map after (2):
+    //   (1) integrate the sites of sites_valid[i_subframe] to the end of the sub-frame
+    //   (2) fixed point of compute_new_sites / integrate the new sites; then the local cost map of trim()
+    //   (3) look the open sites up in the (possibly globally reduced) cost map, close the dominated ones
+    int trim_target() const {
+        return imin((i_subframe + 1) * cfg.n_index_per_subframe, cfg.n_time) - 1;  // index_t_next_subframe - 1
+    }
+
+    int step_trim_integrate() {
+        if (variant != DABRY_TRIMMING) return fail(DABRY_ERR_INVALID, "not a trimming solve");
         bind();
-        const int q = cfg.n_index_per_subframe;
-        const int next = imin((i_subframe + 1) * q, cfg.n_time);  // index_t_next_subframe (:792-794)
-        const int target = next - 1;
         if (int rc = ensure_aux(n_sites)) return rc;
         be.tic();
         ValidFlagPhase vf{S, i_subframe, d_request};
         be.launch(n_sites, vf);
-        int64_t n_list = be.scan_requests(d_request, n_sites, d_offset, d_list);
+        const int64_t n_list = be.scan_requests(d_request, n_sites, d_offset, d_list);
         stats.ms_trim += be.toc();
-        const int32_t* list = d_list;
-        int32_t base = 0;
-        while (n_list > 0) {
-            if (int rc = integrate(list, base, n_list, target)) return rc;
+        if (n_list > 0)
+            if (int rc = integrate(d_list, 0, n_list, trim_target())) return rc;
+        trim_stage = 1;
+        return check();
+    }
+
+    int step_trim_refine() {
+        if (variant != DABRY_TRIMMING || trim_stage != 1) return fail(DABRY_ERR_INVALID, "call step_trim_integrate first");
+        bind();
+        const int target = trim_target();
+        for (;;) {
             if (int rc = resample(target, i_subframe)) return rc;
-            list = nullptr;
-            base = shoot_begin;
-            n_list = shoot_end - shoot_begin;
+            const int64_t n_new = shoot_end - shoot_begin;
+            if (n_new == 0) break;
+            if (int rc = integrate(nullptr, shoot_begin, n_new, target)) return rc;
         }
-        if (int rc = trim(target)) return rc;
+        be.tic();
+        const int q = cfg.n_index_per_subframe;
+        const int start_cm = i_subframe + 1 - cfg.trimming_band_width;
+        // self.sites_valid[start_cm : i_subframe + 1] with Python slice semantics on a list of n_subframes + 1 sets:
+        // a negative start counts from the END of the list, which leaves the slice empty for the first sub-frames
+        const int len = n_subframes() + 1;
+        const int a = start_cm < 0 ? imax(start_cm + len, 0) : imin(start_cm, len);
+        const int b = imin(i_subframe + 1, len);
+        if (int rc = build_cost_map(start_cm * q, target, 0, i_subframe, a, b)) return rc;
+        stats.ms_trim += be.toc();
+        trim_stage = 2;
+        return check();
+    }
+
+    int set_cost_map(const double* map) {
+        be.upload(d_map, map, sizeof(double) * C.cm_nx * C.cm_ny);
+        return check();
+    }
+
+    int step_trim_close() {
+        if (variant != DABRY_TRIMMING || trim_stage != 2) return fail(DABRY_ERR_INVALID, "call step_trim_refine first");
+        bind();
+        be.tic();
+        TrimPhase tp{C, S, d_map, i_subframe, trim_target()};
+        be.launch(n_sites, tp);
+        stats.ms_trim += be.toc();
+        trim_stage = 0;
         ++i_subframe;
         ++round;
         stats.rounds = round;
         return check();
+    }
+
+    int step_trimming() {
+        if (int rc = step_trim_integrate()) return rc;
+        if (int rc = step_trim_refine()) return rc;
+        return step_trim_close();
     }
 
     int finish() {
@@ -928,7 +975,7 @@ private:
     int32_t shoot_begin = 0, shoot_end = 0;
     int variant = DABRY_RESAMPLING;
     int has_ghost = 0;
-    int round = 0, i_subframe = 0;
+    int round = 0, i_subframe = 0, trim_stage = 0;
     int64_t last_new = 0;
     int64_t solution_site = -1;
     double solution_cost = NAN;
@@ -1134,23 +1181,6 @@ private:
             RasterPhase rp{C, S, d_map, (int32_t) n_sites, lo, k_hi, subframe, va, vb, all_sites};
             be.launch(n_sites * (int64_t) (k_hi - lo + 1), rp);
         }
-        return check();
-    }
-
-    // SolverEFTrimming.trim (solver_ef.py:819-841)
-    int trim(int target) {
-        be.tic();
-        const int q = cfg.n_index_per_subframe;
-        const int start_cm = i_subframe + 1 - cfg.trimming_band_width;
-        // self.sites_valid[start_cm : i_subframe + 1] with Python slice semantics on a list of n_subframes + 1 sets:
-        // a negative start counts from the END of the list, which leaves the slice empty for the first sub-frames
-        const int len = n_subframes() + 1;
-        int a = start_cm < 0 ? imax(start_cm + len, 0) : imin(start_cm, len);
-        int b = imin(i_subframe + 1, len);
-        if (int rc = build_cost_map(start_cm * q, target, 0, i_subframe, a, b)) return rc;
-        TrimPhase tp{C, S, d_map, i_subframe, target};
-        be.launch(n_sites, tp);
-        stats.ms_trim += be.toc();
         return check();
     }
 };

@@ -78,6 +78,10 @@ class ShardedResampling:
             handle.call('dabry_step_resample')
         s._invalidate()
         s.depth = s.max_depth
+        return self._finish(handle, fetch)
+
+    def _finish(self, handle, fetch):
+        s = self.solver
         if fetch:
             s.check_solutions()
         else:
@@ -98,3 +102,29 @@ class ShardedResampling:
         self.owner_rank = int(own) if own < 1e17 else -1
         self.total_rk_steps = int(steps.cpu().numpy()[0])
         return self
+
+
+class ShardedTrimming(ShardedResampling):
+    """`SolverEFTrimming` over all ranks: per sub-frame the ring boundary is re-sent (the ghost root grows with its
+    owner) and the 100 x 100 trimming cost map is all_reduce(MIN)-ed (80 kB) before the dominated extremals are
+    closed, so that every rank trims against the global front (solver_ef.py:819-841)."""
+
+    def solve(self, fetch=True):
+        s = self.solver
+        handle = s._ensure_handle()
+        handle.call('dabry_setup', s._VARIANT, nat.dptr(s._root_costates()))
+        for _ in range(s.n_subframes):
+            handle.call('dabry_step_trim_integrate')
+            if self.world > 1:
+                self._exchange_boundary(handle)
+            handle.call('dabry_step_trim_refine')
+            if self.world > 1:
+                local = handle.cost_map(100, 100, full=False)
+                t = self._tensor(local)
+                self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN, group=self.group)
+                merged = np.ascontiguousarray(t.cpu().numpy())
+                handle.call('dabry_set_cost_map', nat.dptr(merged))
+            handle.call('dabry_step_trim_close')
+        s._invalidate()
+        s.i_subframe = s.n_subframes
+        return self._finish(handle, fetch)

@@ -186,6 +186,14 @@ int dabry_step(dabry_solver* h);
  * integrate + connect_to_parents (solver_ef.py:583-587), then compute_new_sites + trim_distance (589-591). */
 int dabry_step_integrate(dabry_solver* h);
 int dabry_step_resample(dabry_solver* h);
+/* The three parts of a Trimming step (solver_ef.py:802-841), for callers that exchange the ring boundary after the
+ * first and all_reduce(MIN) the cost map (dabry_get_cost_map / dabry_set_cost_map) after the second:
+ * integrate sites_valid[i] (803-807) | compute_new_sites fixed point (808-815) + local cost_map_triangle (821-828) |
+ * cost-map lookup and SUBOPTIMAL closure (829-841). */
+int dabry_step_trim_integrate(dabry_solver* h);
+int dabry_step_trim_refine(dabry_solver* h);
+int dabry_step_trim_close(dabry_solver* h);
+int dabry_set_cost_map(dabry_solver* h, const double* map);
 /* check_solutions (solver_ef.py:667-685). */
 int dabry_finish(dabry_solver* h);
 /* setup + all steps + finish: SolverEFResampling.solve (602-608) / SolverEFTrimming.solve (843-857). */

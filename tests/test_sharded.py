@@ -19,11 +19,12 @@ import parity_util as pu
 from dabry_b200 import _native
 _native.use_library(pu.HOSTSIM_LIB)
 from dabry_b200.problem import NavigationProblem
-from dabry_b200.solver_ef import SolverEFResampling
-from dabry_b200.distributed import ShardedResampling
+from dabry_b200.solver_ef import SolverEFResampling, SolverEFTrimming
+from dabry_b200.distributed import ShardedResampling, ShardedTrimming
 dist.init_process_group('gloo')
 pb = NavigationProblem.from_name({case!r}).rescale()
-runner = ShardedResampling(lambda **kw: SolverEFResampling(pb, max_depth={depth}, n_costate_sectors=30, **kw), 30)
+Runner, Solver = (ShardedTrimming, SolverEFTrimming) if {trimming} else (ShardedResampling, SolverEFResampling)
+runner = Runner(lambda **kw: Solver(pb, max_depth={depth}, n_costate_sectors=30, **kw), 30)
 runner.solve()
 s = runner.solver
 rec = {{'rank': runner.rank, 'names': list(s.sites.keys()), 'cost': runner.global_cost, 'owner': runner.owner_rank,
@@ -36,12 +37,13 @@ dist.destroy_process_group()
 '''
 
 
-@pytest.mark.parametrize('case,depth', [('linear', 5), ('moving_vortex', 4)])
-def test_two_rank_sharding_matches_single(case, depth, tmp_path, hostsim):
+@pytest.mark.parametrize('case,depth,trimming', [('linear', 5, False), ('moving_vortex', 4, False),
+                                                 ('gyre', 6, True), ('obstacle', 6, True)])
+def test_two_rank_sharding_matches_single(case, depth, trimming, tmp_path, hostsim):
     import pickle
     import subprocess
     script = tmp_path / 'worker.py'
-    script.write_text(WORKER.format(root=pu.ROOT, case=case, depth=depth, out=str(tmp_path)))
+    script.write_text(WORKER.format(root=pu.ROOT, case=case, depth=depth, out=str(tmp_path), trimming=trimming))
     env = dict(os.environ, MASTER_ADDR='127.0.0.1')
     subprocess.run([sys.executable, '-W', 'ignore', '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
                     '--master-addr', '127.0.0.1', '--master-port', '29611', str(script)], check=True, env=env,
@@ -49,9 +51,9 @@ def test_two_rank_sharding_matches_single(case, depth, tmp_path, hostsim):
     recs = [pickle.load(open(tmp_path / ('rank%d.pkl' % r), 'rb')) for r in range(2)]
 
     from dabry_b200.problem import NavigationProblem
-    from dabry_b200.solver_ef import SolverEFResampling
+    from dabry_b200.solver_ef import SolverEFResampling, SolverEFTrimming
     pb = NavigationProblem.from_name(case).rescale()
-    single = SolverEFResampling(pb, max_depth=depth, n_costate_sectors=30)
+    single = (SolverEFTrimming if trimming else SolverEFResampling)(pb, max_depth=depth, n_costate_sectors=30)
     single.solve()
     # same extremals: the ghost copies are not reported, every site lives on exactly one rank
     names = recs[0]['names'] + recs[1]['names']
