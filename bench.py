@@ -30,7 +30,9 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-BYTES_PER_STEP_DOPRI5_F64 = 2336  # 6 RHS x 8 nodes x 6 scalars x 8 B + 32 B of trajectory output
+# RHS per step x 8 nodes x 6 scalars x bytes per scalar + 32 B of trajectory output
+BYTES_PER_STEP = {('dopri5', 'f64'): 2336, ('dopri5', 'f32'): 1184, ('rk4', 'f64'): 1568, ('rk4', 'f32'): 800}
+BYTES_PER_STEP_DOPRI5_F64 = 2336
 WORKLOADS = ('era5', 'planar', 'gyre')
 
 
@@ -194,6 +196,8 @@ def main():
     ap.add_argument('--cpu-sample-roots', type=int, default=0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--dtype', choices=('f64', 'f32'), default='f64', help="f32 = flow grid stored in fp32 (tolerance 1e-4)")
+    ap.add_argument('--integrator', choices=('dopri5', 'rk4'), default='dopri5')
     args = ap.parse_args()
     if args.roots_per_gpu <= 0:
         args.roots_per_gpu = default_roots(args.workload)
@@ -233,7 +237,7 @@ def main():
 
     def make_solver(device_roots, **extra):
         args_ = dict(n_costate_sectors=n_roots, root_range=root_range, device=local_rank, max_sites=max_sites,
-                     device_roots=device_roots)
+                     device_roots=device_roots, dtype=args.dtype, integrator=args.integrator)
         args_.update(kw)
         args_.update(extra)
         return SolverEFResampling(pb, total, **args_)
@@ -362,10 +366,11 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
-        ach = local_steps * BYTES_PER_STEP_DOPRI5_F64 / (integ_total_ms * 1e-3) / 1e9
+        bytes_per_step = BYTES_PER_STEP[(args.integrator, args.dtype)]
+        ach = local_steps * bytes_per_step / (integ_total_ms * 1e-3) / 1e9
         roofline = {'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
                     'traffic': None, 'kernel': 'phase_kernel<FreeArcPhase<GRID>>', 'peak_source': peak_src,
-                    'algorithmic_bytes_per_step': BYTES_PER_STEP_DOPRI5_F64,
+                    'algorithmic_bytes_per_step': bytes_per_step,
                     'kernel_ms_per_launch': integ_total_ms / args.steps,
                     'note': 'algorithmic bytes (8 nodes x 6 fp64 per RHS, 6 RHS per step, + 32 B output) / measured '
                             'integrate-kernel time; the touched grid region is L2 resident, see DESIGN.md'}
@@ -374,10 +379,10 @@ def main():
         line = {
             'metric': 'extremal_rk_steps_per_sec', 'value': value, 'unit': 'steps/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_dev_ms / args.steps,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64' if args.dtype == 'f64' else 'f64 state / f32 grid', 'data': 'synthetic',
             'config': {'workload': args.workload + ('-small' if args.small else ''), 'flow': descr,
                        'roots_per_gpu': args.roots_per_gpu, 'roots_total': n_roots, 'sites_rank0': n_sites,
-                       'integrator': 'dopri5_scipy', 'n_time': 100, 'max_depth': kw.get('max_depth'),
+                       'integrator': 'dopri5_scipy' if args.integrator == 'dopri5' else 'rk4_fixed', 'n_time': 100, 'max_depth': kw.get('max_depth'),
                        'parallelism': 'theta0-shard x%d' % world, 'l2': 'flushed between steps (256 MiB write)',
                        'timing': 'cuda events on the library stream' if world == 1 else 'barrier-bracketed wall clock, max over ranks',
                        'wall_ms_per_step': total_wall_ms / args.steps,

@@ -97,12 +97,14 @@ __global__ void __launch_bounds__(kScanBlock) scan_pass2(int32_t* __restrict__ b
 __global__ void __launch_bounds__(kScanBlock) scan_pass3(const int32_t* __restrict__ request, int64_t n,
                                                          int32_t* __restrict__ offset,
                                                          const int32_t* __restrict__ block_sum,
-                                                         int32_t* __restrict__ list) {
+                                                         int32_t* __restrict__ list,
+                                                         const int32_t* __restrict__ values, int32_t value_base) {
     const int64_t i = (int64_t) blockIdx.x * kScanBlock + threadIdx.x;
     if (i >= n) return;
     const int32_t o = offset[i] + block_sum[blockIdx.x];
     offset[i] = o;
-    if (list && request[i] >= 0) list[o] = (int32_t) i;
+    // the dense list holds the flagged indices, or values[i] / value_base + i when a value map is given
+    if (list && request[i] >= 0) list[o] = values ? values[i] : value_base + (int32_t) i;
 }
 
 // ---- arrival-time reductions (check_solutions) --------------------------------------------------------------
@@ -236,7 +238,8 @@ public:
     }
 
     // exclusive prefix sum of (request >= 0) into offset; optional dense list of the flagged indices; returns total
-    int64_t scan_requests(const int32_t* request, int64_t n, int32_t* offset, int32_t* list) {
+    int64_t scan_requests(const int32_t* request, int64_t n, int32_t* offset, int32_t* list,
+                          const int32_t* values = nullptr, int32_t value_base = 0) {
         if (n <= 0 || !ok()) return 0;
         const int64_t blocks = (n + kScanBlock - 1) / kScanBlock;
         if (blocks > block_sum_cap_) {
@@ -246,7 +249,7 @@ public:
         }
         scan_pass1<<<(unsigned) blocks, kScanBlock, 0, stream_>>>(request, n, offset, d_block_sum_);
         scan_pass2<<<1, kScanBlock, 0, stream_>>>(d_block_sum_, blocks, (int64_t*) d_small_);
-        scan_pass3<<<(unsigned) blocks, kScanBlock, 0, stream_>>>(request, n, offset, d_block_sum_, list);
+        scan_pass3<<<(unsigned) blocks, kScanBlock, 0, stream_>>>(request, n, offset, d_block_sum_, list, values, value_base);
         launches_ += 3;
         chk(cudaGetLastError(), "scan launch");
         int64_t total = 0;

@@ -11,6 +11,7 @@
 //   check_solutions                             solver_ef.py:667-685             -> finish()
 #pragma once
 #include <limits.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -19,6 +20,12 @@
 #include "../../include/dabry_b200.h"
 #include "site.cuh"
 
+// RK steps per launch of the free-arc kernel, with re-packing of the running extremals in between; 0 = one launch.
+// Measured on B200 (era5, 1.25 M extremals): 0 -> 25.9 ms, 20 -> 28.4, 10 -> 31.0, 5 -> 41.8: the re-packing costs
+// more (lost L1 / theta_0 locality, carry traffic, launch tails) than the idle lanes it removes, so it is off.
+#ifndef DABRY_FREE_CHUNK
+#define DABRY_FREE_CHUNK 0
+#endif
 #ifndef DABRY_INTEGRATE_MIN_BLOCKS
 #define DABRY_INTEGRATE_MIN_BLOCKS 4
 #endif
@@ -119,20 +126,32 @@ struct GhostInitPhase {  // the ghost slot = ring root `ring_index`, evaluated b
 };
 
 template <int FK, int METHOD>
-struct FreeArcPhase {  // the hot kernel: one thread per extremal, free arc with events
+struct FreeArcPhase {  // the hot kernel: one thread per extremal, free arc with events, `budget` RK steps per launch
     static constexpr int kThreads = 128;
     static constexpr int kMinBlocks = DABRY_INTEGRATE_MIN_BLOCKS;  // register cap = 65536 / (128 * kMinBlocks)
     SiteStore S;
     const int32_t* list;  // null: sites [base, base + n)
-    int32_t base, index_t;
+    int32_t base, index_t, budget;
     Counters* counters;
-    int32_t* captured;    // -1 / 0 per work item: does the site need the obstacle kernel
+    int32_t* running;     // -1 / 0 per work item: the arc is parked and continues in the next chunk
     DABRY_HD void operator()(int64_t i) const {
         const int s = list ? list[i] : base + (int) i;
         unsigned attempts = 0, calls = 0;
-        site_free_arc<FK, METHOD>(problem(), S, s, index_t, attempts, calls);
+        site_free_arc<FK, METHOD>(problem(), S, s, index_t, attempts, calls, budget);
         counter_add(&counters->rk_steps, attempts);
         counter_add(&counters->ivp_calls, calls);
+        running[i] = (S.flags[s] & SITE_RUNNING) ? 0 : -1;
+    }
+};
+
+struct CapturedFlagPhase {  // which work items need the obstacle kernel
+    static constexpr int kThreads = 256;
+    SiteStore S;
+    const int32_t* list;
+    int32_t base;
+    int32_t* captured;
+    DABRY_HD void operator()(int64_t i) const {
+        const int s = list ? list[i] : base + (int) i;
         captured[i] = (S.arc_from[s] >= 0 && S.obstacle[s] >= 0) ? 0 : -1;
     }
 };
@@ -489,6 +508,7 @@ public:
         memset(&C, 0, sizeof(C));
         memset(&S, 0, sizeof(S));
         memset(&stats, 0, sizeof(stats));
+        if (const char* env = getenv("DABRY_FREE_CHUNK")) free_chunk = atoi(env);
         times_h.assign(c.times, c.times + c.n_time);
         cfg.times = nullptr;
         P.coords = c.coords;
@@ -526,6 +546,8 @@ public:
         be.free(d_captured);
         be.free(d_cap_offset);
         be.free(d_cap_list);
+        be.free(d_run_a);
+        be.free(d_run_b);
         be.free(d_map);
         be.free(d_arr_index);
         be.free(d_arr_cost);
@@ -963,6 +985,8 @@ private:
     int32_t* d_captured = nullptr;
     int32_t* d_cap_offset = nullptr;
     int32_t* d_cap_list = nullptr;
+    int32_t* d_run_a = nullptr;
+    int32_t* d_run_b = nullptr;
     int64_t work_capacity = 0;
     double* d_map = nullptr;
     int32_t* d_arr_index = nullptr;
@@ -976,6 +1000,7 @@ private:
     int variant = DABRY_RESAMPLING;
     int has_ghost = 0;
     int round = 0, i_subframe = 0, trim_stage = 0;
+    int free_chunk = DABRY_FREE_CHUNK;  // RK steps per launch of the free-arc kernel (0: whole arc in one launch)
     int64_t last_new = 0;
     int64_t solution_site = -1;
     double solution_cost = NAN;
@@ -1034,10 +1059,14 @@ private:
         be.free(d_captured);
         be.free(d_cap_offset);
         be.free(d_cap_list);
+        be.free(d_run_a);
+        be.free(d_run_b);
+        d_run_a = (int32_t*) be.alloc(sizeof(int32_t) * cap);
+        d_run_b = (int32_t*) be.alloc(sizeof(int32_t) * cap);
         d_captured = (int32_t*) be.alloc(sizeof(int32_t) * cap);
         d_cap_offset = (int32_t*) be.alloc(sizeof(int32_t) * cap);
         d_cap_list = (int32_t*) be.alloc(sizeof(int32_t) * cap);
-        if (!d_captured || !d_cap_offset || !d_cap_list) return fail(DABRY_ERR_CAPACITY, "out of device memory (work)");
+        if (!d_captured || !d_cap_offset || !d_cap_list || !d_run_a || !d_run_b) return fail(DABRY_ERR_CAPACITY, "out of device memory (work)");
         work_capacity = cap;
         return DABRY_OK;
     }
@@ -1082,6 +1111,8 @@ private:
         be.free(s.created_subframe); be.free(s.valid_first); be.free(s.valid_last); be.free(s.dyadic);
         be.free(s.next_nb); be.free(s.n_target_events); be.free(s.t_target_events); be.free(s.ivp_status);
         be.free(s.arc_from); be.free(s.enter);
+        be.free(s.carry_t); be.free(s.carry_h); be.free(s.carry_y); be.free(s.carry_f); be.free(s.carry_g);
+        be.free(s.carry_eval_i);
     }
 
     int reserve(int64_t want) {
@@ -1119,6 +1150,9 @@ private:
         ok = ok && grow(S.dyadic, oc, cap, 1, 1) && grow(S.n_target_events, oc, cap, 1, 1);
         ok = ok && grow(S.t_target_events, oc, cap, 1, DABRY_MAX_TARGET_EVENTS) && grow(S.ivp_status, oc, cap, 1, 1);
         ok = ok && grow(S.arc_from, oc, cap, 1, 1) && grow(S.enter, oc, cap, 1, 1);
+        ok = ok && grow(S.carry_t, oc, cap, 1, 1) && grow(S.carry_h, oc, cap, 1, 1) && grow(S.carry_y, oc, cap, 1, 1);
+        ok = ok && grow(S.carry_f, oc, cap, 1, 1) && grow(S.carry_g, oc, cap, 1, DABRY_MAX_EVENTS);
+        ok = ok && grow(S.carry_eval_i, oc, cap, 1, 1);
         if (!ok) return fail(DABRY_ERR_CAPACITY, "out of device memory (site store)");
         S.capacity = (int32_t) cap;
         S.n_time = cfg.n_time;
@@ -1132,10 +1166,25 @@ private:
         if (int rc = ensure_work(n)) return rc;
         be.tic();
         const bool rk4 = cfg.integrator == DABRY_RK4_FIXED;
-        dispatch_field(rk4, [&](auto fk, auto method) {
-            be.launch(n, FreeArcPhase<decltype(fk)::value, decltype(method)::value>{S, list, base, index_t, d_counters,
-                                                                                   d_captured});
-        });
+        // chunks of `free_chunk` RK steps; between chunks the extremals still running are re-packed into a dense
+        // list (ballot/prefix-sum compaction) so that warps stay full after their neighbours were captured
+        const int32_t* cur = list;
+        int32_t cur_base = base;
+        int64_t n_cur = n;
+        int flip = 0;
+        while (n_cur > 0) {
+            dispatch_field(rk4, [&](auto fk, auto method) {
+                be.launch(n_cur, FreeArcPhase<decltype(fk)::value, decltype(method)::value>{
+                                     S, cur, cur_base, index_t, free_chunk, d_counters, d_captured});
+            });
+            if (free_chunk <= 0) break;
+            int32_t* next = flip ? d_run_b : d_run_a;
+            n_cur = be.scan_requests(d_captured, n_cur, d_cap_offset, next, cur, cur_base);
+            cur = next;
+            cur_base = 0;
+            flip ^= 1;
+        }
+        be.launch(n, CapturedFlagPhase{S, list, base, d_captured});
         stats.ms_integrate += be.toc();
         if (C.follow_obstacles) {
             be.tic();

@@ -13,7 +13,19 @@ namespace dabry {
 
 #define DABRY_MAX_EVENTS (1 + DABRY_MAX_OBSTACLES)
 
-enum IvpStatus : int32_t { IVP_FINISHED = 0, IVP_TERMINATED = 1, IVP_FAILED = -1 };
+enum IvpStatus : int32_t { IVP_FINISHED = 0, IVP_TERMINATED = 1, IVP_FAILED = -1, IVP_RUNNING = 2 };
+
+// Everything solve_ivp carries from one step to the next.  With a step budget the driver loop can be left after any
+// step and re-entered later with bit-identical results, which lets the engine re-pack the still-running extremals into
+// full warps between chunks of steps (extremals captured by an obstacle leave early).
+template <int N>
+struct IvpCarry {
+    int32_t started;  // 0: fresh call
+    int32_t eval_i;
+    double t, h_abs;
+    double y[N], f[N];
+    double g[1 + DABRY_MAX_OBSTACLES];
+};
 
 // t_eval = numpy.linspace(t_start, t_end, n)[first:] (solver_ef.py:488, 495): j * step + t_start with the last
 // element overwritten by t_end (numpy/_core/function_base.py linspace); products and sums individually rounded.
@@ -50,20 +62,48 @@ struct IvpResult {
 template <int N, int METHOD, class Rhs, class Events, class Sink>
 DABRY_HD void solve_ivp(const Rhs& rhs, Events& events, Sink& sink, double t0, double tf, const double* y0,
                         const EvalGrid& grid, double max_step, double rtol, double atol, IvpResult<N>& res,
-                        unsigned& n_attempts) {
+                        unsigned& n_attempts, IvpCarry<N>* carry = nullptr, int step_budget = 0) {
     RkState<N> S;
-    if (METHOD == METHOD_RK4) rk4_init<N>(S, rhs, t0, y0, max_step);
-    else rk_init<N>(S, rhs, t0, y0, tf, max_step, rtol, atol);
     const int ne = events.count();
     double g[DABRY_MAX_EVENTS];
-    for (int e = 0; e < ne; ++e) g[e] = events.value(e, t0, y0);
-    int eval_i = grid.first;
+    int eval_i;
+    if (carry && carry->started) {
+        S.t = S.t_old = carry->t;
+        S.h_abs = carry->h_abs;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            S.y[i] = S.y_old[i] = carry->y[i];
+            S.f[i] = carry->f[i];
+        }
+        for (int e = 0; e < ne; ++e) g[e] = carry->g[e];
+        eval_i = carry->eval_i;
+    } else {
+        if (METHOD == METHOD_RK4) rk4_init<N>(S, rhs, t0, y0, max_step);
+        else rk_init<N>(S, rhs, t0, y0, tf, max_step, rtol, atol);
+        for (int e = 0; e < ne; ++e) g[e] = events.value(e, t0, y0);
+        eval_i = grid.first;
+    }
+    int steps_left = step_budget;
     res.status = IVP_FINISHED;
     res.n_emitted = 0;
     res.term_event = -1;
     res.t_term = 0.;
     bool finished = false;
     while (!finished) {
+        if (carry && step_budget > 0 && steps_left-- == 0) {  // budget spent between two steps: park the state
+            carry->started = 1;
+            carry->eval_i = eval_i;
+            carry->t = S.t;
+            carry->h_abs = S.h_abs;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                carry->y[i] = S.y[i];
+                carry->f[i] = S.f[i];
+            }
+            for (int e = 0; e < ne; ++e) carry->g[e] = g[e];
+            res.status = IVP_RUNNING;
+            return;
+        }
         // OdeSolver.step (base.py): a solver already at t_bound finishes without stepping
         if (S.t == tf) {
             S.t_old = S.t;

@@ -87,16 +87,18 @@ template <int N, class Rhs>
 DABRY_HD bool rk_step(RkState<N>& S, const Rhs& rhs, double t_bound, double max_step, double rtol, double atol,
                       unsigned& n_attempts) {
     const double t = S.t;
-    const double min_step = 10. * ulp_above(t);
+    // min_step = 10 ulp(t) (rk.py:119) only matters when the step is within a few ulps of t: 10 ulp(t) <= 4.5e-15 |t|,
+    // so any h_abs above 1e-12 (|t| + 1) is provably larger and nextafter is skipped
     double h_abs = S.h_abs;
+    const double safe = 1e-12 * (fabs(t) + 1.);
     if (h_abs > max_step) h_abs = max_step;
-    else if (h_abs < min_step) h_abs = min_step;
+    else if (!(h_abs > safe) && h_abs < 10. * ulp_above(t)) h_abs = 10. * ulp_above(t);
     bool rejected = false;
     double y_new[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) S.K[0][i] = S.f[i];
     for (;;) {
-        if (h_abs < min_step) return false;
+        if (!(h_abs > safe) && h_abs < 10. * ulp_above(t)) return false;
         double t_new = t + h_abs;
         if (t_new - t_bound > 0.) t_new = t_bound;
         const double h = t_new - t;

@@ -23,7 +23,7 @@ struct Control {
     double u0, u1;
 };
 
-enum SiteFlags : int32_t { SITE_GHOST = 1, SITE_CONNECTED = 2, SITE_PENDING_ENTRY = 4 };
+enum SiteFlags : int32_t { SITE_GHOST = 1, SITE_CONNECTED = 2, SITE_PENDING_ENTRY = 4, SITE_RUNNING = 8 };
 
 struct SiteStore {
     int32_t n_time;
@@ -60,6 +60,13 @@ struct SiteStore {
     int32_t* ivp_status;        // status of the last solve_ivp call of the site (diagnostics)
     int32_t* arc_from;          // grid index the current integrate call started from (-1: nothing to do)
     Sample* enter;              // augmented state at the obstacle entry root, between the two integrate kernels
+    // state of a free arc parked between two chunks of RK steps (IvpCarry)
+    double* carry_t;
+    double* carry_h;
+    Sample* carry_y;
+    Sample* carry_f;
+    double* carry_g;            // [capacity][DABRY_MAX_EVENTS]
+    int32_t* carry_eval_i;
     // time-major addressing: consecutive sites are consecutive in memory at a given grid index, so that a warp
     // of extremals advancing in lockstep writes (and the resampling scan reads) fully coalesced rows
     DABRY_HD int64_t at(int s, int k) const { return (int64_t) k * capacity + s; }
@@ -200,14 +207,30 @@ struct ConstrSink {
 // A terminal obstacle event leaves the entry record (obstacle, t_enter_obs, index_t_obs, state at entry) for part B.
 template <int FK, int METHOD>
 DABRY_HD void site_free_arc(const ProblemDev& P, const SiteStore& S, int s, int index_t, unsigned& n_attempts,
-                            unsigned& n_calls) {
-    const int idx0 = site_index_t(S, s);
-    S.arc_from[s] = -1;
-    if (idx0 >= index_t) return;
+                            unsigned& n_calls, int step_budget) {
+    IvpCarry<4> carry;
+    int idx0;
+    if (S.flags[s] & SITE_RUNNING) {  // re-entry after a chunk of steps
+        idx0 = S.arc_from[s];
+        carry.started = 1;
+        carry.eval_i = S.carry_eval_i[s];
+        carry.t = S.carry_t[s];
+        carry.h_abs = S.carry_h[s];
+        const Sample cy = S.carry_y[s], cf = S.carry_f[s];
+        carry.y[0] = cy.x0; carry.y[1] = cy.x1; carry.y[2] = cy.p0; carry.y[3] = cy.p1;
+        carry.f[0] = cf.x0; carry.f[1] = cf.x1; carry.f[2] = cf.p0; carry.f[3] = cf.p1;
+        for (int e = 0; e <= P.n_obstacles; ++e) carry.g[e] = S.carry_g[(int64_t) s * DABRY_MAX_EVENTS + e];
+    } else {
+        idx0 = site_index_t(S, s);
+        S.arc_from[s] = -1;
+        if (idx0 >= index_t) return;
+        if (index_t - idx0 + 1 <= 1) return;
+        S.arc_from[s] = idx0;
+        if (site_in_obs_at(S, s, idx0)) return;
+        carry.started = 0;
+        ++n_calls;
+    }
     const int n = index_t - idx0 + 1;
-    if (n <= 1) return;
-    S.arc_from[s] = idx0;
-    if (site_in_obs_at(S, s, idx0)) return;
     const Sample y0s = S.xp[S.at(s, idx0)];
     const double y0[4] = {y0s.x0, y0s.x1, y0s.p0, y0s.p1};
     const EvalGrid grid = make_eval_grid(S.times[idx0], S.times[index_t], n, 1);
@@ -215,14 +238,25 @@ DABRY_HD void site_free_arc(const ProblemDev& P, const SiteStore& S, int s, int 
     FreeEvents ev{P, S, s};
     FreeSink sink{S, s, idx0};
     IvpResult<4> res;
-    solve_ivp<4, METHOD>(rhs, ev, sink, grid.at(0), grid.at(n - 1), y0, grid, P.max_step, P.rtol, P.atol, res, n_attempts);
-    ++n_calls;
-    S.ivp_status[s] = res.status;
+    solve_ivp<4, METHOD>(rhs, ev, sink, grid.at(0), grid.at(n - 1), y0, grid, P.max_step, P.rtol, P.atol, res, n_attempts,
+                         &carry, step_budget);
     S.n_samples[s] += res.n_emitted;
+    if (res.status == IVP_RUNNING) {
+        S.flags[s] |= SITE_RUNNING;
+        S.carry_eval_i[s] = carry.eval_i;
+        S.carry_t[s] = carry.t;
+        S.carry_h[s] = carry.h_abs;
+        S.carry_y[s] = Sample{carry.y[0], carry.y[1], carry.y[2], carry.y[3]};
+        S.carry_f[s] = Sample{carry.f[0], carry.f[1], carry.f[2], carry.f[3]};
+        for (int e = 0; e <= P.n_obstacles; ++e) S.carry_g[(int64_t) s * DABRY_MAX_EVENTS + e] = carry.g[e];
+        return;
+    }
+    S.flags[s] &= ~SITE_RUNNING;
+    S.ivp_status[s] = res.status;
     if (res.status == IVP_TERMINATED) {
         S.t_enter_obs[s] = res.t_term;
         S.obstacle[s] = res.term_event;
-        S.index_t_obs[s] = idx0 + res.n_emitted + 1;  // site.index_t + len(traj_free) + 1 (:516)
+        S.index_t_obs[s] = site_index_t(S, s) + 1;  // site.index_t + len(traj_free) + 1 (:516)
         S.enter[s] = Sample{res.y_term[0], res.y_term[1], res.y_term[2], res.y_term[3]};
         S.flags[s] |= SITE_PENDING_ENTRY;
     }

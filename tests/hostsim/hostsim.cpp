@@ -39,12 +39,13 @@ public:
         ++launches_;
         for (int64_t i = 0; i < n; ++i) f(i);
     }
-    int64_t scan_requests(const int32_t* request, int64_t n, int32_t* offset, int32_t* list) {
+    int64_t scan_requests(const int32_t* request, int64_t n, int32_t* offset, int32_t* list,
+                          const int32_t* values = nullptr, int32_t value_base = 0) {
         int32_t acc = 0;
         for (int64_t i = 0; i < n; ++i) {
             offset[i] = acc;
             if (request[i] >= 0) {
-                if (list) list[acc] = (int32_t) i;
+                if (list) list[acc] = values ? values[i] : value_base + (int32_t) i;
                 ++acc;
             }
         }

@@ -179,6 +179,26 @@ test_f32_grid_within_tolerance_hostsim, test_f32_grid_within_tolerance_gpu = _bo
 test_edge_cases_hostsim, test_edge_cases_gpu = _both(edge_cases)
 
 
+def test_chunked_free_arcs_are_bit_identical(hostsim, monkeypatch):
+    """The free-arc kernel can be left after any number of RK steps and re-entered (IvpCarry): a run in chunks of 7
+    steps with re-packing of the running extremals must equal the one-launch run bit for bit."""
+    from dabry_b200.problem import NavigationProblem
+    from dabry_b200.solver_ef import SolverEFResampling
+    pb = NavigationProblem.from_name('moving_vortex').rescale()
+    runs = []
+    for chunk in ('0', '7'):
+        monkeypatch.setenv('DABRY_FREE_CHUNK', chunk)
+        s = SolverEFResampling(pb, max_depth=5)
+        s.solve()
+        runs.append((list(s.sites), {n: (site.traj.states.copy(), site.closure_reason) for n, site in s.sites.items()},
+                     s.native_stats()['rk_steps'], s.native_stats()['kernel_launches']))
+        s.close()
+    assert runs[0][0] == runs[1][0] and runs[0][2] == runs[1][2]
+    assert runs[1][3] > runs[0][3]
+    for n in runs[0][0]:
+        assert np.array_equal(runs[0][1][n][0], runs[1][1][n][0]) and runs[0][1][n][1] == runs[1][1][n][1]
+
+
 def test_library_exports_every_declared_symbol():
     """Every function include/dabry_b200.h declares is exported by the built CUDA library and bound by ctypes (no
     compute call: this runs without a GPU)."""
