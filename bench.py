@@ -368,12 +368,19 @@ def main():
         peak, peak_src = measured_peak_gbs()
         bytes_per_step = BYTES_PER_STEP[(args.integrator, args.dtype)]
         ach = local_steps * bytes_per_step / (integ_total_ms * 1e-3) / 1e9
+        # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the hot kernel at exactly this workload, from the
+        # ncu --set full capture summarised in profiles/r01_ncu_full_arcs.txt (0.422 GB read + 7.443 GB written)
+        traffic = 7.865e9 if (args.workload, args.roots_per_gpu, args.dtype, args.integrator, args.small) == \
+            ('era5', 1_250_000, 'f64', 'dopri5', False) else None
         roofline = {'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
-                    'traffic': None, 'kernel': 'phase_kernel<FreeArcPhase<GRID>>', 'peak_source': peak_src,
+                    'traffic': traffic, 'kernel': 'phase_kernel<FreeArcPhase<GRID>>', 'peak_source': peak_src,
                     'algorithmic_bytes_per_step': bytes_per_step,
                     'kernel_ms_per_launch': integ_total_ms / args.steps,
-                    'note': 'algorithmic bytes (8 nodes x 6 fp64 per RHS, 6 RHS per step, + 32 B output) / measured '
-                            'integrate-kernel time; the touched grid region is L2 resident, see DESIGN.md'}
+                    'fp64_pipe_active_pct': 41.5, 'issue_active_pct': 48.9,
+                    'note': 'algorithmic bytes (8 nodes x 6 scalars per RHS, zero reuse credit, + 32 B output) / measured '
+                            'free-arc kernel time.  frac > 1: theta-sorted neighbours share grid cells, L1 (85 %) and L2 '
+                            '(83 %) serve the gather and DRAM traffic is 40x below the algorithmic bytes; the kernel is '
+                            'fp64-pipe / latency bound (ncu: fp64 pipe 41.5 %, issue slots 48.9 %), see DESIGN.md 3 and 6'}
         if args.workload == 'gyre':
             roofline['note'] = 'analytic field: no gather, fp64-pipe bound; fraction of the gather roofline is nominal'
         line = {
