@@ -125,7 +125,7 @@ struct GhostInitPhase {  // the ghost slot = ring root `ring_index`, evaluated b
     }
 };
 
-template <int FK, int METHOD>
+template <int FK, int METHOD, bool CHUNKED>
 struct FreeArcPhase {  // the hot kernel: one thread per extremal, free arc with events, `budget` RK steps per launch
     static constexpr int kThreads = 128;
     static constexpr int kMinBlocks = DABRY_INTEGRATE_MIN_BLOCKS;  // register cap = 65536 / (128 * kMinBlocks)
@@ -137,10 +137,10 @@ struct FreeArcPhase {  // the hot kernel: one thread per extremal, free arc with
     DABRY_HD void operator()(int64_t i) const {
         const int s = list ? list[i] : base + (int) i;
         unsigned attempts = 0, calls = 0;
-        site_free_arc<FK, METHOD>(problem(), S, s, index_t, attempts, calls, budget);
+        site_free_arc<FK, METHOD, CHUNKED>(problem(), S, s, index_t, attempts, calls, budget);
         counter_add(&counters->rk_steps, attempts);
         counter_add(&counters->ivp_calls, calls);
-        running[i] = (S.flags[s] & SITE_RUNNING) ? 0 : -1;
+        if (CHUNKED) running[i] = (S.flags[s] & SITE_RUNNING) ? 0 : -1;
     }
 };
 
@@ -1174,8 +1174,13 @@ private:
         int flip = 0;
         while (n_cur > 0) {
             dispatch_field(rk4, [&](auto fk, auto method) {
-                be.launch(n_cur, FreeArcPhase<decltype(fk)::value, decltype(method)::value>{
-                                     S, cur, cur_base, index_t, free_chunk, d_counters, d_captured});
+                constexpr int kField = decltype(fk)::value, kMethod = decltype(method)::value;
+                if (free_chunk > 0)
+                    be.launch(n_cur, FreeArcPhase<kField, kMethod, true>{S, cur, cur_base, index_t, free_chunk,
+                                                                         d_counters, d_captured});
+                else
+                    be.launch(n_cur, FreeArcPhase<kField, kMethod, false>{S, cur, cur_base, index_t, 0, d_counters,
+                                                                          d_captured});
             });
             if (free_chunk <= 0) break;
             int32_t* next = flip ? d_run_b : d_run_a;

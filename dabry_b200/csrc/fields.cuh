@@ -16,11 +16,6 @@
 #pragma once
 #include "common.cuh"
 
-#ifndef DABRY_STAGE_GATHER
-#define DABRY_STAGE_GATHER 0
-#endif
-#define DABRY_GATHER_THREADS 128  // block size of every kernel that samples the grid
-
 namespace dabry {
 
 // FIELD_GRID_F32: the same pair records stored in fp32 (48 B per node, three 16-byte loads); arithmetic stays fp64
@@ -327,31 +322,9 @@ DABRY_HD void grid_eval(const GridDesc& G, double t, double x0, double x1, Flow&
         const double* n01 = G.data + (size_t) (row0 + j1) * 12;
         const double* n10 = G.data + (size_t) (row1 + j0) * 12;
         const double* n11 = G.data + (size_t) (row1 + j1) * 12;
-#if defined(__CUDA_ARCH__) && DABRY_STAGE_GATHER
-        // EXPERIMENT, off by default (measured 3x SLOWER on B200): all 24 sixteen-byte pieces of the 4
-        // node records go global -> shared with cp.async (LDGSTS) so that they are all in flight at once.  The 48 KB
-        // of staging per block shrink L1 to ~36 KB per SM, which the register spills of the integrator live in;
-        // and an fp32 grid (half the loads) is no faster than fp64, i.e. the gather is not the limiter.
-        __shared__ double2 stage[24 * DABRY_GATHER_THREADS];
-        double2* mine = stage + threadIdx.x;
-        const double* src[4] = {n00, n01, n10, n11};
-#pragma unroll
-        for (int nd = 0; nd < 4; ++nd)
-#pragma unroll
-            for (int c = 0; c < 6; ++c) {
-                const unsigned dst = (unsigned) __cvta_generic_to_shared(mine + (nd * 6 + c) * DABRY_GATHER_THREADS);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src[nd] + 2 * c) : "memory");
-            }
-        asm volatile("cp.async.wait_all;" ::: "memory");
-#pragma unroll
-        for (int c = 0; c < 6; ++c) {
-            const double2 a = mine[(0 * 6 + c) * DABRY_GATHER_THREADS], b = mine[(1 * 6 + c) * DABRY_GATHER_THREADS];
-            const double2 d = mine[(2 * 6 + c) * DABRY_GATHER_THREADS], e = mine[(3 * 6 + c) * DABRY_GATHER_THREADS];
-            const double lo = ((w00 * a.x + w01 * b.x) + w10 * d.x) + w11 * e.x;
-            const double hi = ((w00 * a.y + w01 * b.y) + w10 * d.y) + w11 * e.y;
-            acc[c] = wt_lo * lo + wt_hi * hi;
-        }
-#else
+        // Two alternatives were measured on B200 and dropped: staging the 24 pieces in shared memory
+        // with cp.async (3x slower: the 48 KB per block shrink the L1 the integrator's spills live in) and issuing
+        // the loads through ordered inline PTX (ptxas re-schedules them; no change).
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
             const D2 a = load_pair(n00 + 2 * c), b = load_pair(n01 + 2 * c);
@@ -360,7 +333,6 @@ DABRY_HD void grid_eval(const GridDesc& G, double t, double x0, double x1, Flow&
             const double hi = ((w00 * a.y + w01 * b.y) + w10 * d.y) + w11 * e.y;
             acc[c] = wt_lo * lo + wt_hi * hi;
         }
-#endif
     }
     o.w0 = acc[0];
     o.w1 = acc[1];

@@ -205,12 +205,12 @@ struct ConstrSink {
 //
 // Part A - the free arc (solver_ef.py:482-504): solve_ivp on the augmented system with the target / obstacle events.
 // A terminal obstacle event leaves the entry record (obstacle, t_enter_obs, index_t_obs, state at entry) for part B.
-template <int FK, int METHOD>
+template <int FK, int METHOD, bool CHUNKED>
 DABRY_HD void site_free_arc(const ProblemDev& P, const SiteStore& S, int s, int index_t, unsigned& n_attempts,
                             unsigned& n_calls, int step_budget) {
     IvpCarry<4> carry;
     int idx0;
-    if (S.flags[s] & SITE_RUNNING) {  // re-entry after a chunk of steps
+    if (CHUNKED && (S.flags[s] & SITE_RUNNING)) {  // re-entry after a chunk of steps
         idx0 = S.arc_from[s];
         carry.started = 1;
         carry.eval_i = S.carry_eval_i[s];
@@ -239,9 +239,9 @@ DABRY_HD void site_free_arc(const ProblemDev& P, const SiteStore& S, int s, int 
     FreeSink sink{S, s, idx0};
     IvpResult<4> res;
     solve_ivp<4, METHOD>(rhs, ev, sink, grid.at(0), grid.at(n - 1), y0, grid, P.max_step, P.rtol, P.atol, res, n_attempts,
-                         &carry, step_budget);
+                         CHUNKED ? &carry : nullptr, CHUNKED ? step_budget : 0);
     S.n_samples[s] += res.n_emitted;
-    if (res.status == IVP_RUNNING) {
+    if (CHUNKED && res.status == IVP_RUNNING) {
         S.flags[s] |= SITE_RUNNING;
         S.carry_eval_i[s] = carry.eval_i;
         S.carry_t[s] = carry.t;
@@ -251,7 +251,7 @@ DABRY_HD void site_free_arc(const ProblemDev& P, const SiteStore& S, int s, int 
         for (int e = 0; e <= P.n_obstacles; ++e) S.carry_g[(int64_t) s * DABRY_MAX_EVENTS + e] = carry.g[e];
         return;
     }
-    S.flags[s] &= ~SITE_RUNNING;
+    if (CHUNKED) S.flags[s] &= ~SITE_RUNNING;
     S.ivp_status[s] = res.status;
     if (res.status == IVP_TERMINATED) {
         S.t_enter_obs[s] = res.t_term;
