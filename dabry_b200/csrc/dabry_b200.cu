@@ -184,6 +184,12 @@ public:
         cudaEventCreate(&tot0_);
         cudaEventCreate(&tot1_);
         if (!chk(cudaMalloc(&d_small_, 64), "cudaMalloc")) return false;
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
         return true;
     }
 
@@ -192,11 +198,13 @@ public:
     uint64_t launches() const { return launches_; }
     cudaStream_t stream() const { return stream_; }
 
+    // Stream-ordered allocations from the device's default memory pool with an unbounded release threshold: freed
+    // blocks stay cached in the pool, so a second solver of the same shape (the usual pattern: one handle per
+    // solve() call) does not pay cudaMalloc / cudaFree again (measured 13 - 300 ms per solve for 10 GB of site store).
     void* alloc(size_t bytes) {
         if (bytes == 0) bytes = 8;
-        cudaSetDevice(device_);
         void* p = nullptr;
-        if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        if (cudaMallocAsync(&p, bytes, stream_) != cudaSuccess) {
             cudaGetLastError();
             return nullptr;
         }
@@ -204,10 +212,7 @@ public:
     }
     template <class T>
     void free(T* p) {
-        if (p) {
-            cudaStreamSynchronize(stream_);
-            cudaFree((void*) p);
-        }
+        if (p) cudaFreeAsync((void*) p, stream_);
     }
     void upload(void* d, const void* h, size_t bytes) {
         chk(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, stream_), "H2D copy");
