@@ -196,6 +196,8 @@ def main():
     ap.add_argument('--cpu-sample-roots', type=int, default=0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--shard-block', type=int, default=5000,
+                    help='N > 1: block-cyclic theta_0 sharding with this many roots per block (0: contiguous ranges)')
     ap.add_argument('--dtype', choices=('f64', 'f32'), default='f64', help="f32 = flow grid stored in fp32 (tolerance 1e-4)")
     ap.add_argument('--integrator', choices=('dopri5', 'rk4'), default='dopri5')
     args = ap.parse_args()
@@ -230,14 +232,15 @@ def main():
 
     pb, total, kw, descr = build_problem(args.workload, args.small)
     n_roots = args.roots_per_gpu * world
-    root_range = shard_range(n_roots, rank, world) if world > 1 else None
-    count = root_range[1] if root_range else n_roots
+    shard = (rank, world, args.shard_block) if world > 1 and args.shard_block > 0 else None
+    root_range = shard_range(n_roots, rank, world) if world > 1 and shard is None else None
+    count = n_roots // world if shard else (root_range[1] if root_range else n_roots)
     cap_factor = 1.02 if kw.get('max_depth', 1) == 1 else 2.5
     max_sites = int(count * cap_factor) + 4096
 
     def make_solver(device_roots, **extra):
-        args_ = dict(n_costate_sectors=n_roots, root_range=root_range, device=local_rank, max_sites=max_sites,
-                     device_roots=device_roots, dtype=args.dtype, integrator=args.integrator)
+        args_ = dict(n_costate_sectors=n_roots, root_range=root_range, shard=shard, device=local_rank,
+                     max_sites=max_sites, device_roots=device_roots, dtype=args.dtype, integrator=args.integrator)
         args_.update(kw)
         args_.update(extra)
         return SolverEFResampling(pb, total, **args_)
@@ -256,8 +259,8 @@ def main():
                 return self
         runner = _Solo(make_solver(device_roots=True))
     else:
-        runner = ShardedResampling(lambda **k: make_solver(device_roots=True), n_roots, device=local_rank)
-        runner.solver.root_range = root_range
+        runner = ShardedResampling(lambda **k: make_solver(device_roots=True), n_roots, device=local_rank,
+                                   block=args.shard_block or None)
     solver = runner.solver
     handle = solver._ensure_handle()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')  # > 126 MB L2
@@ -390,7 +393,8 @@ def main():
             'config': {'workload': args.workload + ('-small' if args.small else ''), 'flow': descr,
                        'roots_per_gpu': args.roots_per_gpu, 'roots_total': n_roots, 'sites_rank0': n_sites,
                        'integrator': 'dopri5_scipy' if args.integrator == 'dopri5' else 'rk4_fixed', 'n_time': 100, 'max_depth': kw.get('max_depth'),
-                       'parallelism': 'theta0-shard x%d' % world, 'l2': 'flushed between steps (256 MiB write)',
+                       'parallelism': 'theta0-shard x%d (%s)' % (world, 'block-cyclic, %d roots per block' % args.shard_block
+                                                                 if shard else 'contiguous'), 'l2': 'flushed between steps (256 MiB write)',
                        'timing': 'cuda events on the library stream' if world == 1 else 'barrier-bracketed wall clock, max over ranks',
                        'wall_ms_per_step': total_wall_ms / args.steps,
                        'phase_ms_rank0': {k: round(v, 3) for k, v in phases.items()},

@@ -31,6 +31,7 @@ class Config(C.Structure):
         ('n_index_per_subframe', C.c_int32), ('trimming_band_width', C.c_int32),
         ('cost_map_nx', C.c_int32), ('cost_map_ny', C.c_int32),
         ('n_roots', C.c_int64), ('root_offset', C.c_int64), ('root_count', C.c_int64), ('max_sites', C.c_int64),
+        ('shard_block', C.c_int64), ('shard_world', C.c_int64),
         ('t_init', C.c_double), ('max_step', C.c_double), ('rtol', C.c_double), ('atol', C.c_double),
         ('srf', C.c_double), ('x_init', C.c_double * 2), ('x_target', C.c_double * 2),
         ('target_radius', C.c_double), ('max_dist', C.c_double), ('bl', C.c_double * 2), ('tr', C.c_double * 2),
@@ -113,6 +114,7 @@ SIGNATURES = {
     'dabry_get_stats': (C.c_int, [_H, C.POINTER(Stats)]),
     'dabry_get_flow_max_norm': (C.c_int, [_H, c_double_p]),
     'dabry_boundary_doubles': (C.c_int, [_H, C.POINTER(C.c_int64)]),
+    'dabry_boundary_count': (C.c_int, [_H, C.POINTER(C.c_int64)]),
     'dabry_export_boundary': (C.c_int, [_H, c_double_p]),
     'dabry_import_boundary': (C.c_int, [_H, c_double_p]),
     'dabry_eval_rhs': (C.c_int, [_H, C.c_int64, c_double_p, c_double_p, c_double_p]),

@@ -202,6 +202,13 @@ int dabry_boundary_doubles(dabry_solver* h, int64_t* n) {
     return DABRY_OK;
 }
 
+int dabry_boundary_count(dabry_solver* h, int64_t* n) {
+    DABRY_GUARD(h);
+    if (!n) return DABRY_ERR_INVALID;
+    *n = E.boundary_count();
+    return DABRY_OK;
+}
+
 int dabry_export_boundary(dabry_solver* h, double* packed) {
     DABRY_GUARD(h);
     return E.export_boundary(packed);

@@ -80,17 +80,20 @@ struct InitRootsPhase {
     const double* costates;  // [count][2] or null
     double x0, x1, t_init, dtheta;
     int64_t root_offset, root_count, n_roots;
+    int64_t block, block_stride;  // local root j is ring root root_offset + (j / block) * block_stride + j % block
     int32_t max_depth, has_ghost;
+    DABRY_HD int64_t ring_index(int64_t j) const { return root_offset + (j / block) * block_stride + j % block; }
     DABRY_HD void operator()(int64_t i) const {
         const int s = (int) i;
         site_reset(S, s);
+        const int64_t g = ring_index(i);
         double p0, p1;
         if (costates) {
             p0 = costates[2 * i];
             p1 = costates[2 * i + 1];
         } else {
             // theta = linspace(0, 2 pi, n, endpoint=False)[g] = g * (2 pi / n); costate 1000 (cos, sin) (:465-467)
-            const double th = mul_rn((double) (root_offset + i), dtheta);
+            const double th = mul_rn((double) g, dtheta);
             double sn, cs;
             sincos(th, &sn, &cs);
             p0 = 1000. * cs;
@@ -99,25 +102,33 @@ struct InitRootsPhase {
         const int64_t o = S.at(s, 0);
         S.xp[o] = Sample{x0, x1, p0, p1};
         S.tt[o] = t_init;
-        S.dyadic[s] = (root_offset + i) << max_depth;
+        S.dyadic[s] = g << max_depth;
         S.valid_first[s] = 0;
         S.valid_last[s] = 0;
-        // ring neighbour at grid index 0 (:468-469); the last local root points at the ghost slot when the ring
-        // is sharded over several handles
+        // ring neighbour at grid index 0 (:468-469); when the ring is sharded over several handles the last root of
+        // every local block points at that block's ghost slot (a copy of the next rank's root, slots after the roots)
         int nb = s + 1;
-        if (i == root_count - 1) nb = has_ghost ? (int) root_count : 0;
+        if (has_ghost) {
+            if (i % block == block - 1) nb = (int) (root_count + i / block);
+        } else if (i == root_count - 1) {
+            nb = 0;
+        }
         S.next_nb[o] = nb;
     }
 };
 
-struct GhostInitPhase {  // the ghost slot = ring root `ring_index`, evaluated by the same code as the local roots
-    static constexpr int kThreads = 32;
+struct GhostInitPhase {  // ghost k = the ring root after the last root of local block k, not yet integrated
+    static constexpr int kThreads = 64;
     InitRootsPhase roots;
-    int64_t slot, ring_index;
-    DABRY_HD void operator()(int64_t) const {
+    DABRY_HD void operator()(int64_t k) const {
+        const int64_t slot = roots.root_count + k;
+        const int64_t g = (roots.ring_index(k * roots.block + roots.block - 1) + 1) % roots.n_roots;
         InitRootsPhase h = roots;
         h.costates = nullptr;
-        h.root_offset = ring_index - slot;
+        h.has_ghost = 0;
+        h.block = (int64_t) 1 << 60;  // identity mapping: ring index = root_offset + slot
+        h.block_stride = 0;
+        h.root_offset = g - slot;
         h.root_count = -1;
         h(slot);
         h.S.flags[slot] = SITE_GHOST;
@@ -456,13 +467,18 @@ struct GatherRecordPhase {
 
 // multi-GPU ring boundary: one site <-> a packed buffer of n_time * 7 + 16 doubles
 #define DABRY_BOUNDARY_HEADER 16
-struct BoundaryPhase {
+struct BoundaryPhase {  // one work item per (packet, time index)
     static constexpr int kThreads = 128;
     SiteStore S;
-    int32_t site, do_import, n_time;
-    double* buf;
-    DABRY_HD void operator()(int64_t k) const {
-        const int64_t o = S.at(site, (int) k);
+    int32_t do_import, n_time;
+    int64_t root_count, block, packet;  // export: first root of local block k; import: ghost slot root_count + k
+    double* all;
+    DABRY_HD void operator()(int64_t i) const {
+        const int64_t pk = i / n_time;
+        const int k = (int) (i % n_time);
+        const int site = (int) (do_import ? root_count + pk : pk * block);
+        double* buf = all + pk * packet;
+        const int64_t o = S.at(site, k);
         double* row = buf + DABRY_BOUNDARY_HEADER + 7 * k;
         if (!do_import) {
             row[0] = S.xp[o].x0; row[1] = S.xp[o].x1; row[2] = S.xp[o].p0; row[3] = S.xp[o].p1;
@@ -646,12 +662,20 @@ public:
     int setup(int variant_, const double* costates) {
         bind();
         if (P.field.kind < 0) return fail(DABRY_ERR_INVALID, "no flow field set");
-        if (cfg.root_count < 1 || cfg.root_offset < 0 || cfg.root_offset + cfg.root_count > cfg.n_roots)
+        // theta_0 shard of this handle: contiguous [root_offset, root_offset + root_count) (shard_block == 0), or
+        // block-cyclic: blocks of shard_block roots, every shard_world-th block of the ring starting at root_offset
+        shard_b = cfg.shard_block > 0 ? cfg.shard_block : cfg.root_count;
+        const int64_t world = cfg.shard_block > 0 ? cfg.shard_world : 1;
+        if (cfg.root_count < 1 || cfg.root_offset < 0 || shard_b < 1 || cfg.root_count % shard_b != 0 || world < 1)
+            return fail(DABRY_ERR_INVALID, "bad root range");
+        n_blocks = cfg.root_count / shard_b;
+        if (cfg.root_offset + (n_blocks - 1) * world * shard_b + shard_b > cfg.n_roots)
             return fail(DABRY_ERR_INVALID, "bad root range");
         variant = variant_;
         C.follow_obstacles = variant == DABRY_SIMPLE ? 0 : 1;
         has_ghost = cfg.root_count < cfg.n_roots ? 1 : 0;
-        const int64_t n0 = cfg.root_count + has_ghost;
+        const int64_t n_ghosts = has_ghost ? n_blocks : 0;
+        const int64_t n0 = cfg.root_count + n_ghosts;
         int64_t cap = cfg.max_sites > 0 ? cfg.max_sites : 2 * n0 + 1024;
         if (cap < n0) cap = n0;
         n_sites = 0;
@@ -671,12 +695,10 @@ public:
             be.upload(d_cost, costates, sizeof(double) * 2 * cfg.root_count);
         }
         InitRootsPhase ph{S, d_cost, cfg.x_init[0], cfg.x_init[1], cfg.t_init, 2 * M_PI / (double) cfg.n_roots,
-                          cfg.root_offset, cfg.root_count, cfg.n_roots, cfg.max_depth, has_ghost};
+                          cfg.root_offset, cfg.root_count, cfg.n_roots, shard_b, world * shard_b, cfg.max_depth,
+                          has_ghost};
         be.launch(cfg.root_count, ph);
-        if (has_ghost) {  // placeholder until dabry_import_boundary: the un-integrated next root of the ring
-            GhostInitPhase g{ph, cfg.root_count, (cfg.root_offset + cfg.root_count) % cfg.n_roots};
-            be.launch(1, g);
-        }
+        if (has_ghost) be.launch(n_blocks, GhostInitPhase{ph});  // placeholders until dabry_import_boundary
         be.sync();
         be.free(d_cost);
         n_sites = n0;
@@ -921,22 +943,26 @@ public:
     double solution_cost_value() const { return solution_cost; }
 
     // ---- multi-GPU boundary ----
+    // one packet per local block: export = the FIRST root of every block, import = the ghost of every block
     int64_t boundary_doubles() const { return (int64_t) cfg.n_time * 7 + DABRY_BOUNDARY_HEADER; }
+    int64_t boundary_count() const { return n_blocks; }
     int export_boundary(double* packed) {
-        const int64_t n = boundary_doubles();
+        const int64_t n = boundary_doubles() * n_blocks;
         double* d = (double*) scratch(sizeof(double) * n);
-        BoundaryPhase ph{S, 0, 0, cfg.n_time, d};
-        be.launch(cfg.n_time, ph);
+        if (!d) return fail(DABRY_ERR_CAPACITY, "out of device memory");
+        BoundaryPhase ph{S, 0, cfg.n_time, cfg.root_count, shard_b, boundary_doubles(), d};
+        be.launch(n_blocks * cfg.n_time, ph);
         be.download(packed, d, sizeof(double) * n);
         return check();
     }
     int import_boundary(const double* packed) {
         if (!has_ghost) return fail(DABRY_ERR_INVALID, "this handle owns the whole ring: no ghost site");
-        const int64_t n = boundary_doubles();
+        const int64_t n = boundary_doubles() * n_blocks;
         double* d = (double*) scratch(sizeof(double) * n);
+        if (!d) return fail(DABRY_ERR_CAPACITY, "out of device memory");
         be.upload(d, packed, sizeof(double) * n);
-        BoundaryPhase ph{S, (int32_t) cfg.root_count, 1, cfg.n_time, d};
-        be.launch(cfg.n_time, ph);
+        BoundaryPhase ph{S, 1, cfg.n_time, cfg.root_count, shard_b, boundary_doubles(), d};
+        be.launch(n_blocks * cfg.n_time, ph);
         return check();
     }
 
@@ -999,6 +1025,7 @@ private:
     int32_t shoot_begin = 0, shoot_end = 0;
     int variant = DABRY_RESAMPLING;
     int has_ghost = 0;
+    int64_t shard_b = 1, n_blocks = 1;
     int round = 0, i_subframe = 0, trim_stage = 0;
     int free_chunk = DABRY_FREE_CHUNK;  // RK steps per launch of the free-arc kernel (0: whole arc in one launch)
     int64_t last_new = 0;

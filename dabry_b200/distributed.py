@@ -28,14 +28,19 @@ class ShardedResampling:
     >>> runner.solve(); runner.global_cost, runner.owner_rank
     """
 
-    def __init__(self, make_solver, n_roots: int, device=None, group=None):
+    def __init__(self, make_solver, n_roots: int, device=None, group=None, block=None):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.root_range = shard_range(n_roots, self.rank, self.world)
-        kwargs = dict(root_range=self.root_range if self.world > 1 else None)
+        # block=None: one contiguous theta_0 range per rank.  block=B: block-cyclic, B roots per block - extremals
+        # heading out of the domain are captured early, so contiguous ranges are unevenly loaded
+        if block and self.world > 1:
+            kwargs = dict(shard=(self.rank, self.world, block))
+        else:
+            kwargs = dict(root_range=self.root_range if self.world > 1 else None)
         if device is not None:
             kwargs['device'] = device
         self.solver = make_solver(**kwargs)
@@ -51,19 +56,24 @@ class ShardedResampling:
         return t
 
     def _exchange_boundary(self, handle):
-        """first root of rank r -> ghost of rank r - 1 (ring)."""
+        """first root of every block of rank r -> ghost of the preceding block, which lives on rank r - 1 (ring)."""
         import ctypes as C
-        n = C.c_int64()
-        handle.call('dabry_boundary_doubles', C.byref(n))
-        send = np.empty(n.value)
+        size, count = C.c_int64(), C.c_int64()
+        handle.call('dabry_boundary_doubles', C.byref(size))
+        handle.call('dabry_boundary_count', C.byref(count))
+        send = np.empty((count.value, size.value))
         handle.call('dabry_export_boundary', nat.dptr(send))
-        t_send, t_recv = self._tensor(send), self._tensor(np.empty(n.value))
+        t_send, t_recv = self._tensor(send), self._tensor(np.empty_like(send))
         dist = self.dist
         ops = [dist.P2POp(dist.isend, t_send, (self.rank - 1) % self.world, self.group),
                dist.P2POp(dist.irecv, t_recv, (self.rank + 1) % self.world, self.group)]
         for req in dist.batch_isend_irecv(ops):
             req.wait()
-        recv = np.ascontiguousarray(t_recv.cpu().numpy())
+        recv = t_recv.cpu().numpy()
+        # block k of rank r is followed by block k of rank r + 1, except on the last rank: by block k + 1 of rank 0
+        if self.rank == self.world - 1:
+            recv = np.roll(recv, -1, axis=0)
+        recv = np.ascontiguousarray(recv)
         handle.call('dabry_import_boundary', nat.dptr(recv))
 
     def solve(self, fetch=True):

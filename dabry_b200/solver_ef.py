@@ -234,7 +234,8 @@ class SolverEF(ABC):
                  t_init: Optional[float] = None, n_costate_norm: int = 10, costate_norm_bounds=(0., 1.),
                  target_radius: Optional[float] = None, abs_max_step: Optional[float] = None,
                  rel_max_step: Optional[float] = 0.01, *, device: int = 0, max_sites: int = 0,
-                 root_range: Optional[tuple] = None, integrator: str = 'dopri5', dtype: str = 'f64'):
+                 root_range: Optional[tuple] = None, shard: Optional[tuple] = None, integrator: str = 'dopri5',
+                 dtype: str = 'f64'):
         if mode not in self._ALL_MODES:
             raise ValueError('Mode %s is not defined' % mode)
         if mode == 'energy':
@@ -283,6 +284,15 @@ class SolverEF(ABC):
         self.device = device
         self.max_sites = max_sites
         self.root_range = root_range
+        # shard = (rank, world, block): block-cyclic theta_0 sharding - this solver owns blocks of `block` roots, every
+        # world-th block of the ring starting with block `rank` (balances the load between ranks); root_range =
+        # (offset, count) is the contiguous alternative
+        self.shard = shard
+        if shard is not None:
+            rank, world, block = shard
+            if n_costate_sectors % (world * block) != 0:
+                raise ValueError('n_costate_sectors must be a multiple of world * block')
+            self.root_range = (rank * block, n_costate_sectors // world)
         self._event_names = list(self.events.keys())
         self._handle: Optional[nat.Handle] = None
         self._stale = True
@@ -353,6 +363,8 @@ class SolverEF(ABC):
         offset, count = (0, n_roots) if self.root_range is None else self.root_range
         cfg.root_offset, cfg.root_count = offset, count
         cfg.max_sites = self.max_sites
+        if self.shard is not None:
+            cfg.shard_block, cfg.shard_world = self.shard[2], self.shard[1]
         cfg.t_init = self.t_init
         cfg.max_step = self.max_int_step
         cfg.rtol, cfg.atol = 1e-3, 1e-6
@@ -485,9 +497,17 @@ class SolverEFResampling(SolverEF):
         if self.device_roots:
             return None
         n = self.n_costate_sectors
-        offset, count = (0, n) if self.root_range is None else self.root_range
-        theta = np.linspace(0, 2 * np.pi, n, endpoint=False)[offset:offset + count]
+        theta = np.linspace(0, 2 * np.pi, n, endpoint=False)[self._ring_indices()]
         return nat.f64(1000 * np.stack((np.cos(theta), np.sin(theta)), -1))
+
+    def _ring_indices(self):
+        """Ring (global) index of every local root, in slot order."""
+        offset, count = (0, self.n_costate_sectors) if self.root_range is None else self.root_range
+        j = np.arange(count)
+        if self.shard is None:
+            return offset + j
+        _, world, block = self.shard
+        return offset + (j // block) * (world * block) + j % block
 
     @property
     def _ff_max_norm(self):

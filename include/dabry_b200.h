@@ -56,6 +56,9 @@ typedef struct dabry_config {
     int64_t root_offset;          /* multi-GPU: this handle owns roots [root_offset, root_offset + root_count) */
     int64_t root_count;           /* == n_roots on a single GPU */
     int64_t max_sites;            /* initial capacity in sites (0: 2 * root_count + 1024); storage grows on demand */
+    int64_t shard_block;          /* 0: contiguous shard.  > 0: block-cyclic - this handle owns blocks of shard_block roots,
+                                     every shard_world-th block of the ring, the first one starting at root_offset */
+    int64_t shard_world;
     double t_init;                /* cost = t - t_init (solver_ef.py:501) */
     double max_step;              /* solver.max_int_step (solver_ef.py:335-337) */
     double rtol, atol;            /* scipy defaults 1e-3, 1e-6 (rk.py:86) */
@@ -221,10 +224,13 @@ int dabry_get_stats(dabry_solver* h, dabry_stats* out);
 int dabry_get_flow_max_norm(dabry_solver* h, double* out);
 
 /* ---- multi-GPU ring boundary ---------------------------------------------------------------- */
-/* The last root of rank r needs the first root of rank r+1 as its next neighbour (solver_ef.py:468-469).
- * export: this handle's FIRST root trajectory, packed [n_time][4] (x, p) + [n_time] times; import: installs the
- * packed trajectory as a ghost site that is the next neighbour of this handle's LAST root. */
+/* The last root of every local block needs the next root of the ring, owned by the next rank, as its neighbour
+ * (solver_ef.py:468-469).  A packet = one root trajectory, dabry_boundary_doubles doubles ([n_time][7] samples +
+ * header); a handle has dabry_boundary_count packets (= its number of blocks; 1 for a contiguous shard).
+ * export: the FIRST root of each local block, in block order.  import: packets installed as the ghost sites of the
+ * local blocks, in block order (the caller routes rank r+1's packets to rank r, see dabry_b200/distributed.py). */
 int dabry_boundary_doubles(dabry_solver* h, int64_t* n);
+int dabry_boundary_count(dabry_solver* h, int64_t* n);
 int dabry_export_boundary(dabry_solver* h, double* packed);
 int dabry_import_boundary(dabry_solver* h, const double* packed);
 

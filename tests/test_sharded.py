@@ -24,7 +24,7 @@ from dabry_b200.distributed import ShardedResampling, ShardedTrimming
 dist.init_process_group('gloo')
 pb = NavigationProblem.from_name({case!r}).rescale()
 Runner, Solver = (ShardedTrimming, SolverEFTrimming) if {trimming} else (ShardedResampling, SolverEFResampling)
-runner = Runner(lambda **kw: Solver(pb, max_depth={depth}, n_costate_sectors=30, **kw), 30)
+runner = Runner(lambda **kw: Solver(pb, max_depth={depth}, n_costate_sectors=30, **kw), 30, block={block})
 runner.solve()
 s = runner.solver
 rec = {{'rank': runner.rank, 'names': list(s.sites.keys()), 'cost': runner.global_cost, 'owner': runner.owner_rank,
@@ -37,13 +37,14 @@ dist.destroy_process_group()
 '''
 
 
-@pytest.mark.parametrize('case,depth,trimming', [('linear', 5, False), ('moving_vortex', 4, False),
-                                                 ('gyre', 6, True), ('obstacle', 6, True)])
-def test_two_rank_sharding_matches_single(case, depth, trimming, tmp_path, hostsim):
+@pytest.mark.parametrize('case,depth,trimming,block', [('linear', 5, False, None), ('moving_vortex', 4, False, 5),
+                                                       ('gyre', 6, True, None), ('obstacle', 6, True, 3),
+                                                       ('three_vortices', 5, False, 1)])
+def test_two_rank_sharding_matches_single(case, depth, trimming, block, tmp_path, hostsim):
     import pickle
     import subprocess
     script = tmp_path / 'worker.py'
-    script.write_text(WORKER.format(root=pu.ROOT, case=case, depth=depth, out=str(tmp_path), trimming=trimming))
+    script.write_text(WORKER.format(root=pu.ROOT, case=case, depth=depth, out=str(tmp_path), trimming=trimming, block=block))
     env = dict(os.environ, MASTER_ADDR='127.0.0.1')
     subprocess.run([sys.executable, '-W', 'ignore', '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
                     '--master-addr', '127.0.0.1', '--master-port', '29611', str(script)], check=True, env=env,
