@@ -497,7 +497,7 @@ class SolverEFResampling(SolverEF):
         if self.device_roots:
             return None
         n = self.n_costate_sectors
-        theta = np.linspace(0, 2 * np.pi, n, endpoint=False)[self._ring_indices()]
+        theta = np.linspace(0, 2 * np.pi, n, endpoint=False)[self._ring_indices() % n]  # the library validates the range
         return nat.f64(1000 * np.stack((np.cos(theta), np.sin(theta)), -1))
 
     def _ring_indices(self):
