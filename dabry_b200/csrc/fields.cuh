@@ -275,7 +275,8 @@ DABRY_HD F4 load_quad(const float* p) {
 // clipped pair (lo, hi) of ANY time position is one record and the time lerp needs no select: k < 0 -> both frame 0,
 // k >= nt - 1 -> both frame nt - 1.  Positions use the host-computed reciprocal spacing (one rounding away from the
 // reference's division; continuous in the result).
-template <bool F32>
+// JAC = false: only the two value components are sampled (boundary-following arcs and events need no Jacobian).
+template <bool F32, bool JAC>
 DABRY_HD void grid_eval(const GridDesc& G, double t, double x0, double x1, Flow& o) {
     double wt_lo = 1., wt_hi = 0.;
     int frame = 1;
@@ -299,7 +300,7 @@ DABRY_HD void grid_eval(const GridDesc& G, double t, double x0, double x1, Flow&
     const unsigned row1 = ((unsigned) frame * (unsigned) G.nx + (unsigned) i1) * (unsigned) G.ny;
     // corner weights (w_t * w_x) * w_y in the reference; here the time factor is applied per node last
     const double w00 = wx_lo * wy_lo, w01 = wx_lo * wy_hi, w10 = wx_hi * wy_lo, w11 = wx_hi * wy_hi;
-    double acc[6];
+    double acc[6] = {0., 0., 0., 0., 0., 0.};
     if (F32) {
         const float* base = reinterpret_cast<const float*>(G.data);
         const float* n00 = base + (size_t) (row0 + j0) * 12;
@@ -307,7 +308,7 @@ DABRY_HD void grid_eval(const GridDesc& G, double t, double x0, double x1, Flow&
         const float* n10 = base + (size_t) (row1 + j0) * 12;
         const float* n11 = base + (size_t) (row1 + j1) * 12;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {  // one float4 = two components x (frame k, frame k + 1)
+        for (int c = 0; c < (JAC ? 3 : 1); ++c) {  // one float4 = two components x (frame k, frame k + 1)
             const F4 a = load_quad(n00 + 4 * c), b = load_quad(n01 + 4 * c);
             const F4 d = load_quad(n10 + 4 * c), e = load_quad(n11 + 4 * c);
             const double lo0 = ((w00 * a.x + w01 * b.x) + w10 * d.x) + w11 * e.x;
@@ -326,7 +327,7 @@ DABRY_HD void grid_eval(const GridDesc& G, double t, double x0, double x1, Flow&
         // with cp.async (3x slower: the 48 KB per block shrink the L1 the integrator's spills live in) and issuing
         // the loads through ordered inline PTX (ptxas re-schedules them; no change).
 #pragma unroll
-        for (int c = 0; c < 6; ++c) {
+        for (int c = 0; c < (JAC ? 6 : 2); ++c) {
             const D2 a = load_pair(n00 + 2 * c), b = load_pair(n01 + 2 * c);
             const D2 d = load_pair(n10 + 2 * c), e = load_pair(n11 + 2 * c);
             const double lo = ((w00 * a.x + w01 * b.x) + w10 * d.x) + w11 * e.x;
@@ -343,15 +344,15 @@ DABRY_HD void grid_eval(const GridDesc& G, double t, double x0, double x1, Flow&
 }
 
 // WrapperFF.value / d_value (flowfield.py:538-544) around either family.
-template <int FK>
+template <int FK, bool JAC = true>
 DABRY_HD void field_eval(const FieldDesc& F, double t, double x0, double x1, Flow& o) {
     const double tt = F.time_origin + t * F.scale_time;
     const double xx0 = F.wbl[0] + x0 * F.scale_length;
     const double xx1 = F.wbl[1] + x1 * F.scale_length;
     if (FK == FIELD_GRID) {
-        grid_eval<false>(F.grid, tt, xx0, xx1, o);
+        grid_eval<false, JAC>(F.grid, tt, xx0, xx1, o);
     } else if (FK == FIELD_GRID_F32) {
-        grid_eval<true>(F.grid, tt, xx0, xx1, o);
+        grid_eval<true, JAC>(F.grid, tt, xx0, xx1, o);
     } else {
         Flow acc = {0., 0., 0., 0., 0., 0.};
         for (int l = 0; l < F.n_leaves; ++l) {

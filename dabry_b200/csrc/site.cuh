@@ -288,7 +288,7 @@ DABRY_HD void site_obstacle_arcs(const ProblemDev& P, const SiteStore& S, int s,
         const double sign = trigo ? 1. : -1.;
         const double d0 = -sign * g1, d1 = sign * g0;
         Flow f;
-        field_eval<FK>(P.field, t_enter, ye.x0, ye.x1, f);
+        field_eval<FK, false>(P.field, t_enter, ye.x0, ye.x1, f);
         bool tracked = false;
         if (possible_direction(f.w0, f.w1, d0, d1, P.srf)) {
             // t_eval[t_eval > t_enter_obs][0]  (solver_ef.py:528-530)
