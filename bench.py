@@ -33,7 +33,7 @@ import numpy as np  # noqa: E402
 # RHS per step x 8 nodes x 6 scalars x bytes per scalar + 32 B of trajectory output
 BYTES_PER_STEP = {('dopri5', 'f64'): 2336, ('dopri5', 'f32'): 1184, ('rk4', 'f64'): 1568, ('rk4', 'f32'): 800}
 BYTES_PER_STEP_DOPRI5_F64 = 2336
-WORKLOADS = ('era5', 'planar', 'gyre')
+WORKLOADS = ('era5', 'planar', 'gyre', 'regional')
 
 
 def build_problem(workload, small=False):
@@ -61,11 +61,27 @@ def build_problem(workload, small=False):
     if workload == 'gyre':
         pb = NavigationProblem.from_name('gyre').rescale()
         return pb, 1.0, dict(max_depth=1), 'gyre analytic'
+    if workload == 'regional':
+        # BASELINE config 5: what NavigationProblem.from_database builds (0.5 deg box, 3-hourly frames over 48 h) plus
+        # one circular obstacle and one circular penalty; SolverEFTrimming
+        from dabry_b200.obstacle import CircleObs
+        from dabry_b200.penalty import CirclePenalty
+        from dabry_b200.misc import Utils
+        shape = (5, 41, 23) if small else (17, 181, 101)
+        sc = synthetic.regional_constrained(*shape)
+        ff = DiscreteFF(sc.values, sc.bounds, Coords.GCS, force_no_diff=True)
+        obstacles = [CircleObs(np.array(c), float(r)) for c, r in sc.circle_obstacles]
+        c, r, a = sc.circle_penalty
+        pb = NavigationProblem(ff, sc.x_init, sc.x_target, sc.srf, bl=sc.bl, tr=sc.tr, obstacles=obstacles,
+                               penalty=CirclePenalty(np.array(c), float(r), float(a)), name='regional').rescale()
+        t_gc = Utils.distance(sc.x_init, sc.x_target, Coords.GCS) / sc.srf
+        total = 1.1 * t_gc * (sc.srf / Utils.EARTH_RADIUS)
+        return pb, total, dict(max_depth=3, trimming=True), 'regional_constrained %dx%dx%d gcs + obstacle + penalty' % shape
     raise ValueError(workload)
 
 
 def default_roots(workload):
-    return {'era5': 1_250_000, 'planar': 1 << 19, 'gyre': 100_000}[workload]
+    return {'era5': 1_250_000, 'planar': 1 << 19, 'gyre': 100_000, 'regional': 500_000}[workload]
 
 
 class ClockSampler(threading.Thread):
@@ -268,9 +284,12 @@ def main():
 
     from dabry_b200 import _native as nat
     from dabry_b200.distributed import shard_range
-    from dabry_b200.solver_ef import SolverEFResampling
+    from dabry_b200.solver_ef import SolverEFResampling, SolverEFTrimming
 
     pb, total, kw, descr = build_problem(args.workload, args.small)
+    trimming = bool(kw.pop('trimming', False))
+    solver_cls = SolverEFTrimming if trimming else SolverEFResampling
+    variant = nat.TRIMMING if trimming else nat.RESAMPLING
     n_roots = args.roots_per_gpu * world
     shard = (rank, world, args.shard_block) if world > 1 and args.shard_block > 0 else None
     root_range = shard_range(n_roots, rank, world) if world > 1 and shard is None else None
@@ -283,10 +302,10 @@ def main():
                      max_sites=max_sites, device_roots=device_roots, dtype=args.dtype, integrator=args.integrator)
         args_.update(kw)
         args_.update(extra)
-        return SolverEFResampling(pb, total, **args_)
+        return solver_cls(pb, total, **args_)
 
     # ---- resident arm: grid uploaded once, K timed solves ----
-    from dabry_b200.distributed import ShardedResampling
+    from dabry_b200.distributed import ShardedResampling, ShardedTrimming
     if world == 1:
         # single process: ShardedResampling needs a process group only for its collectives
         class _Solo:
@@ -295,12 +314,12 @@ def main():
 
             def solve(self, fetch=True):
                 h = self.solver._ensure_handle()
-                h.call('dabry_solve', nat.RESAMPLING, nat.dptr(self.solver._root_costates()))
+                h.call('dabry_solve', variant, nat.dptr(self.solver._root_costates()))
                 return self
         runner = _Solo(make_solver(device_roots=True))
     else:
-        runner = ShardedResampling(lambda **k: make_solver(device_roots=True), n_roots, device=local_rank,
-                                   block=args.shard_block or None)
+        runner = (ShardedTrimming if trimming else ShardedResampling)(
+            lambda **k: make_solver(device_roots=True), n_roots, device=local_rank, block=args.shard_block or None)
     solver = runner.solver
     handle = solver._ensure_handle()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')  # > 126 MB L2
@@ -432,7 +451,7 @@ def main():
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64' if args.dtype == 'f64' else 'f64 state / f32 grid', 'data': 'synthetic',
             'config': {'workload': args.workload + ('-small' if args.small else ''), 'flow': descr,
                        'roots_per_gpu': args.roots_per_gpu, 'roots_total': n_roots, 'sites_rank0': n_sites,
-                       'integrator': 'dopri5_scipy' if args.integrator == 'dopri5' else 'rk4_fixed', 'n_time': 100, 'max_depth': kw.get('max_depth'),
+                       'integrator': 'dopri5_scipy' if args.integrator == 'dopri5' else 'rk4_fixed', 'n_time': 100, 'max_depth': kw.get('max_depth'), 'solver': solver_cls.__name__,
                        'parallelism': 'theta0-shard x%d (%s)' % (world, 'block-cyclic, %d roots per block' % args.shard_block
                                                                  if shard else 'contiguous'), 'l2': 'flushed between steps (256 MiB write)',
                        'timing': 'cuda events on the library stream' if world == 1 else 'barrier-bracketed wall clock, max over ranks',
