@@ -492,10 +492,15 @@ DABRY_HD void raster_triangle(const SolverParams& C, double* map, double p10, do
     const double xmin = dmin(p10, dmin(p20, p30)), xmax = dmax(p10, dmax(p20, p30));
     const double ymin = dmin(p11, dmin(p21, p31)), ymax = dmax(p11, dmax(p21, p31));
     if (!(xmin == xmin) || !(xmax == xmax) || !(ymin == ymin) || !(ymax == ymax)) return;
-    const int i_lo = iclamp((int) floor((xmin - C.bl[0]) / sx) - 1, 0, C.cm_nx - 1);
-    const int i_hi = iclamp((int) ceil((xmax - C.bl[0]) / sx) + 1, 0, C.cm_nx - 1);
-    const int j_lo = iclamp((int) floor((ymin - C.bl[1]) / sy) - 1, 0, C.cm_ny - 1);
-    const int j_hi = iclamp((int) ceil((ymax - C.bl[1]) / sy) + 1, 0, C.cm_ny - 1);
+    // grid nodes that can lie inside: linspace index range of the bounding box, widened by 1e-6 of a cell against
+    // the rounding of the index mapping (the inside test below is the reference's, evaluated per node).  On a dense
+    // front almost every triangle is smaller than a cell and the range is empty.
+    const double ax = (xmin - C.bl[0]) / sx, bx = (xmax - C.bl[0]) / sx;
+    const double ay = (ymin - C.bl[1]) / sy, by = (ymax - C.bl[1]) / sy;
+    if (!(bx >= -1. && ax <= (double) C.cm_nx && by >= -1. && ay <= (double) C.cm_ny)) return;
+    const int i_lo = imax((int) ceil(ax - 1e-6), 0), i_hi = imin((int) floor(bx + 1e-6), C.cm_nx - 1);
+    const int j_lo = imax((int) ceil(ay - 1e-6), 0), j_hi = imin((int) floor(by + 1e-6), C.cm_ny - 1);
+    if (i_lo > i_hi || j_lo > j_hi) return;
     for (int i = i_lo; i <= i_hi; ++i) {
         const double gx = map_coord(C.bl[0], C.tr[0], C.cm_nx, i);
         for (int j = j_lo; j <= j_hi; ++j) {

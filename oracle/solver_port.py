@@ -193,6 +193,7 @@ class Port:
         self.solution_cost = float('nan')
         self.n_ivp = 0
         self.n_rk = 0
+        self.cost_maps = []
 
     # ---- naming -------------------------------------------------------------------------------------------
     def name_of(self, index):
@@ -466,6 +467,7 @@ class Port:
                 pool.update({id(s): s for s in group})
             cmap = self.cost_map(pool.values(), start * self.q, target)
             self.last_cost_map = cmap
+            self.cost_maps.append(cmap)
             considered = {id(s): s for s in valid[i]}
             considered.update({id(s): s for s in created[i]})
             bl = np.asarray(self.pb.bl, dtype=float)

@@ -138,6 +138,40 @@ def f32_grid_within_tolerance():
         b.close()
 
 
+def trimming_cost_map_matches_oracle():
+    """K4: the device rasteriser (bounding-box triangles + atomicMin) against the oracle's whole-grid numpy
+    rasterisation (cost_map_triangle, solver_ef.py:860-889) on the last sub-frame of a trimming solve, and
+    `cost_map_triangle()` over all sites."""
+    from cases import CASES, build_problem, solver_args
+    from dabry_b200.solver_ef import SolverEFTrimming
+    from solver_port import Port
+    for key in ('regional_constrained_T', 'big_rankine_T'):
+        case = CASES[key]
+        pb = build_problem(case, pu.package_api())
+        args, kw = solver_args(case, pb)
+        port = Port(*args, **kw).run_trimming()
+        solver = SolverEFTrimming(*args, **kw)
+        solver.setup()
+        n_finite = 0
+        for i in range(solver.n_subframes):  # the partial cost map of every sub-frame (solver_ef.py:825-828)
+            solver.step()
+            mine, ref = solver._partial_cost_map, port.cost_maps[i]
+            assert np.array_equal(np.isfinite(mine), np.isfinite(ref)), (key, i)
+            fin = np.isfinite(ref)
+            n_finite += int(fin.sum())
+            if fin.any():
+                assert np.max(np.abs(mine[fin] - ref[fin])) < 1e-10, (key, i)
+        assert n_finite > 500
+        solver.check_solutions()
+        assert list(solver.sites) == list(port.sites)
+        full = solver.cost_map_triangle()
+        ref_full = port.cost_map(port.sites.values(), 0, port.n_time - 1)
+        assert np.array_equal(np.isfinite(full), np.isfinite(ref_full))
+        fin = np.isfinite(ref_full)
+        assert np.max(np.abs(full[fin] - ref_full[fin])) < 1e-10
+        solver.close()
+
+
 def edge_cases():
     from dabry_b200 import _native as nat
     from dabry_b200.problem import NavigationProblem
@@ -177,6 +211,7 @@ test_analytic_rhs_parity_hostsim, test_analytic_rhs_parity_gpu = _both(analytic_
 test_rk4_fixed_matches_oracle_hostsim, test_rk4_fixed_matches_oracle_gpu = _both(rk4_fixed_matches_oracle)
 test_f32_grid_within_tolerance_hostsim, test_f32_grid_within_tolerance_gpu = _both(f32_grid_within_tolerance)
 test_edge_cases_hostsim, test_edge_cases_gpu = _both(edge_cases)
+test_trimming_cost_map_hostsim, test_trimming_cost_map_gpu = _both(trimming_cost_map_matches_oracle)
 
 
 def test_chunked_free_arcs_are_bit_identical(hostsim, monkeypatch):
