@@ -276,25 +276,8 @@ DABRY_HD F4 load_quad(const float* p) {
 // k >= nt - 1 -> both frame nt - 1.  Positions use the host-computed reciprocal spacing (one rounding away from the
 // reference's division; continuous in the result).
 // JAC = false: only the two value components are sampled (boundary-following arcs and events need no Jacobian).
-struct GridCell {  // where a point sits in the grid: the 4 node records and the interpolation weights
-    unsigned n00, n01, n10, n11;  // record indices
-    double w00, w01, w10, w11, wt_lo, wt_hi;
-};
-
-DABRY_HD void prefetch_l1(const void* p) {
-#if defined(__CUDA_ARCH__)
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-#else
-    (void) p;
-#endif
-}
-
-// Locates the point and PREFETCHES the cache lines of its 4 node records into L1.  A prefetch has no destination
-// register, so - unlike the loads, of which the 128-register budget keeps only 2-3 in flight - all lines of a
-// right-hand side are requested at once; the caller puts its grid-independent arithmetic (trigonometry of the
-// latitude, costate normalisation) between locate and gather, and the loads then hit L1.
-template <bool F32>
-DABRY_HD void grid_locate(const GridDesc& G, double t, double x0, double x1, GridCell& cell) {
+template <bool F32, bool JAC>
+DABRY_HD void grid_eval(const GridDesc& G, double t, double x0, double x1, Flow& o) {
     double wt_lo = 1., wt_hi = 0.;
     int frame = 1;
     if (G.unsteady) {
@@ -315,45 +298,15 @@ DABRY_HD void grid_locate(const GridDesc& G, double t, double x0, double x1, Gri
     // record indices fit 32 bits (checked at upload); one 64-bit multiply per node for the byte offset
     const unsigned row0 = ((unsigned) frame * (unsigned) G.nx + (unsigned) i0) * (unsigned) G.ny;
     const unsigned row1 = ((unsigned) frame * (unsigned) G.nx + (unsigned) i1) * (unsigned) G.ny;
-    cell.n00 = row0 + j0;
-    cell.n01 = row0 + j1;
-    cell.n10 = row1 + j0;
-    cell.n11 = row1 + j1;
     // corner weights (w_t * w_x) * w_y in the reference; here the time factor is applied per node last
-    cell.w00 = wx_lo * wy_lo;
-    cell.w01 = wx_lo * wy_hi;
-    cell.w10 = wx_hi * wy_lo;
-    cell.w11 = wx_hi * wy_hi;
-    cell.wt_lo = wt_lo;
-    cell.wt_hi = wt_hi;
-    const size_t rec = F32 ? 48 : 96;  // bytes per record; the two nodes of a row are adjacent (or the same) records
-    const char* base = reinterpret_cast<const char*>(G.data);
-    const char* r0 = base + (size_t) cell.n00 * rec;
-    const char* r1 = base + (size_t) cell.n10 * rec;
-    prefetch_l1(r0);
-    prefetch_l1(r0 + 2 * rec - 1);
-    prefetch_l1(r1);
-    prefetch_l1(r1 + 2 * rec - 1);
-    if (!F32) {
-        prefetch_l1(r0 + 128);
-        prefetch_l1(r1 + 128);
-    }
-}
-
-template <bool F32, bool JAC>
-DABRY_HD void grid_gather(const GridDesc& G, const GridCell& cell, Flow& o) {
-    const double w00 = cell.w00, w01 = cell.w01, w10 = cell.w10, w11 = cell.w11;
-    const double wt_lo = cell.wt_lo, wt_hi = cell.wt_hi;
-    const unsigned row0 = cell.n00, row1 = cell.n10;
-    const unsigned j0 = 0, j1 = cell.n01 - cell.n00;
-    const unsigned k0 = 0, k1 = cell.n11 - cell.n10;
+    const double w00 = wx_lo * wy_lo, w01 = wx_lo * wy_hi, w10 = wx_hi * wy_lo, w11 = wx_hi * wy_hi;
     double acc[6] = {0., 0., 0., 0., 0., 0.};
     if (F32) {
         const float* base = reinterpret_cast<const float*>(G.data);
         const float* n00 = base + (size_t) (row0 + j0) * 12;
         const float* n01 = base + (size_t) (row0 + j1) * 12;
-        const float* n10 = base + (size_t) (row1 + k0) * 12;
-        const float* n11 = base + (size_t) (row1 + k1) * 12;
+        const float* n10 = base + (size_t) (row1 + j0) * 12;
+        const float* n11 = base + (size_t) (row1 + j1) * 12;
         // dtype F32: grid positions and weights are fp64 (a float position would quantise the weights to 1e-5 of a
         // cell), the 48 multiply-adds of the interpolation run in fp32 on the fp32 node data
         const float f00 = (float) w00, f01 = (float) w01, f10 = (float) w10, f11 = (float) w11;
@@ -372,11 +325,11 @@ DABRY_HD void grid_gather(const GridDesc& G, const GridCell& cell, Flow& o) {
     } else {
         const double* n00 = G.data + (size_t) (row0 + j0) * 12;
         const double* n01 = G.data + (size_t) (row0 + j1) * 12;
-        const double* n10 = G.data + (size_t) (row1 + k0) * 12;
-        const double* n11 = G.data + (size_t) (row1 + k1) * 12;
-        // Two alternatives were measured on B200 and dropped: staging the 24 pieces in shared memory
-        // with cp.async (3x slower: the 48 KB per block shrink the L1 the integrator's spills live in) and issuing
-        // the loads through ordered inline PTX (ptxas re-schedules them; no change).
+        const double* n10 = G.data + (size_t) (row1 + j0) * 12;
+        const double* n11 = G.data + (size_t) (row1 + j1) * 12;
+        // Measured on B200 and dropped: staging the 24 pieces in shared memory with cp.async (3x slower:
+        // the 48 KB per block shrink the L1 the integrator's spills live in), ordered inline-PTX loads (ptxas
+        // re-schedules them), and prefetch.global.L1 of the cell ahead of the latitude trigonometry (+6 %).
 #pragma unroll
         for (int c = 0; c < (JAC ? 6 : 2); ++c) {
             const D2 a = load_pair(n00 + 2 * c), b = load_pair(n01 + 2 * c);
@@ -394,34 +347,21 @@ DABRY_HD void grid_gather(const GridDesc& G, const GridCell& cell, Flow& o) {
     o.j11 = acc[5];
 }
 
-// WrapperFF.value / d_value (flowfield.py:538-544) around either family, in two halves: `field_locate` applies the
-// wrapper's change of variables and (grid families) locates + prefetches the cell; `field_finish` samples / evaluates
-// and applies the speed scalings.  `field_eval` = both.
-struct FieldPoint {
-    double t, x0, x1;
-    GridCell cell;
-};
-
-template <int FK>
-DABRY_HD void field_locate(const FieldDesc& F, double t, double x0, double x1, FieldPoint& pt) {
-    pt.t = F.time_origin + t * F.scale_time;
-    pt.x0 = F.wbl[0] + x0 * F.scale_length;
-    pt.x1 = F.wbl[1] + x1 * F.scale_length;
-    if (FK == FIELD_GRID) grid_locate<false>(F.grid, pt.t, pt.x0, pt.x1, pt.cell);
-    else if (FK == FIELD_GRID_F32) grid_locate<true>(F.grid, pt.t, pt.x0, pt.x1, pt.cell);
-}
-
+// WrapperFF.value / d_value (flowfield.py:538-544) around either family.
 template <int FK, bool JAC = true>
-DABRY_HD void field_finish(const FieldDesc& F, const FieldPoint& pt, Flow& o) {
+DABRY_HD void field_eval(const FieldDesc& F, double t, double x0, double x1, Flow& o) {
+    const double tt = F.time_origin + t * F.scale_time;
+    const double xx0 = F.wbl[0] + x0 * F.scale_length;
+    const double xx1 = F.wbl[1] + x1 * F.scale_length;
     if (FK == FIELD_GRID) {
-        grid_gather<false, JAC>(F.grid, pt.cell, o);
+        grid_eval<false, JAC>(F.grid, tt, xx0, xx1, o);
     } else if (FK == FIELD_GRID_F32) {
-        grid_gather<true, JAC>(F.grid, pt.cell, o);
+        grid_eval<true, JAC>(F.grid, tt, xx0, xx1, o);
     } else {
         Flow acc = {0., 0., 0., 0., 0., 0.};
         for (int l = 0; l < F.n_leaves; ++l) {
             Flow f;
-            leaf_eval(F.leaves[l], F.tables, pt.t, pt.x0, pt.x1, f);
+            leaf_eval(F.leaves[l], F.tables, tt, xx0, xx1, f);
             const double c = F.leaves[l].coeff;
             if (l == 0) {
                 acc.w0 = c * f.w0; acc.w1 = c * f.w1;
@@ -439,13 +379,6 @@ DABRY_HD void field_finish(const FieldDesc& F, const FieldPoint& pt, Flow& o) {
     o.j01 *= F.scaler_dspeed;
     o.j10 *= F.scaler_dspeed;
     o.j11 *= F.scaler_dspeed;
-}
-
-template <int FK, bool JAC = true>
-DABRY_HD void field_eval(const FieldDesc& F, double t, double x0, double x1, Flow& o) {
-    FieldPoint pt;
-    field_locate<FK>(F, t, x0, x1, pt);
-    field_finish<FK, JAC>(F, pt, o);
 }
 
 }  // namespace dabry
