@@ -136,6 +136,10 @@ struct GhostInitPhase {  // ghost k = the ring root after the last root of local
     }
 };
 
+#ifndef DABRY_TRACE_FREE_ARC  // analysis hook of tests/hostsim (per-extremal attempt counts); nothing in the product
+#define DABRY_TRACE_FREE_ARC(site, attempts)
+#endif
+
 template <int FK, int METHOD, bool CHUNKED>
 struct FreeArcPhase {  // the hot kernel: one thread per extremal, free arc with events, `budget` RK steps per launch
     static constexpr int kThreads = 128;
@@ -149,6 +153,7 @@ struct FreeArcPhase {  // the hot kernel: one thread per extremal, free arc with
         const int s = list ? list[i] : base + (int) i;
         unsigned attempts = 0, calls = 0;
         site_free_arc<FK, METHOD, CHUNKED>(problem(), S, s, index_t, attempts, calls, budget);
+        DABRY_TRACE_FREE_ARC(s, attempts);
         counter_add(&counters->rk_steps, attempts);
         counter_add(&counters->ivp_calls, calls);
         if (CHUNKED) running[i] = (S.flags[s] & SITE_RUNNING) ? 0 : -1;

@@ -12,6 +12,17 @@
 #include <chrono>
 #include <string>
 
+// DABRY_HOSTSIM_TRACE=<file>: one "site attempts" line per free arc (lane-imbalance analysis, profiles/lane_imbalance.py)
+#include <stdio.h>
+static FILE* hostsim_trace_file() {
+    static FILE* f = getenv("DABRY_HOSTSIM_TRACE") ? fopen(getenv("DABRY_HOSTSIM_TRACE"), "w") : nullptr;
+    return f;
+}
+#define DABRY_TRACE_FREE_ARC(site, attempts)                                                    \
+    do {                                                                                        \
+        if (FILE* tf_ = hostsim_trace_file()) { fprintf(tf_, "%d %u\n", (int) (site), (unsigned) (attempts)); fflush(tf_); } \
+    } while (0)
+
 #include "../../dabry_b200/csrc/engine.cuh"
 
 namespace dabry {
