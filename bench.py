@@ -389,6 +389,8 @@ def main():
     if not args.no_e2e:
         inner = getattr(pb.model.ff, 'ff', pb.model.ff)
         h2d = int((inner.values.nbytes if hasattr(inner, 'values') else 0) + 16 * count)
+        if hasattr(inner, 'pin_memory'):
+            inner.pin_memory()  # the step's input (the flow samples) lives in pinned host memory, as the contract asks
 
         def e2e_step():
             s = make_solver(device_roots=False)

@@ -88,6 +88,8 @@ SIGNATURES = {
     'dabry_destroy': (None, [_H]),
     'dabry_last_error': (C.c_char_p, [_H]),
     'dabry_backend_name': (C.c_char_p, []),
+    'dabry_host_register': (C.c_int, [C.c_void_p, C.c_size_t]),
+    'dabry_host_unregister': (C.c_int, [C.c_void_p]),
     'dabry_set_flow_grid': (C.c_int, [_H, c_double_p, c_double_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                       c_double_p, c_double_p, C.POINTER(Wrapper)]),
     'dabry_set_flow_program': (C.c_int, [_H, C.POINTER(Leaf), C.c_int32, c_double_p, C.c_int64, C.POINTER(Wrapper)]),
@@ -167,6 +169,33 @@ def iptr(a):
 
 def f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class PinnedArray:
+    """Page-locks a C-contiguous numpy array in place (dabry_host_register) for as long as this object lives, so that
+    its H2D copies run at the PCIe rate.  The array itself is untouched and stays usable as plain numpy."""
+
+    def __init__(self, array):
+        if not (isinstance(array, np.ndarray) and array.flags['C_CONTIGUOUS'] and array.flags['WRITEABLE']):
+            raise ValueError('pinning needs a writeable C-contiguous numpy array')
+        self.array = array
+        self._lib = library()
+        self._ptr = array.ctypes.data
+        rc = self._lib.dabry_host_register(self._ptr, array.nbytes)
+        if rc != 0:
+            self._ptr = None
+            raise NativeError(rc, 'dabry_host_register failed (no CUDA device, or the range is already pinned)')
+
+    def release(self):
+        if getattr(self, '_ptr', None):
+            self._lib.dabry_host_unregister(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
 
 
 class Handle:

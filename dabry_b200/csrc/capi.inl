@@ -21,6 +21,16 @@ int dabry_abi_version(void) { return DABRY_ABI_VERSION; }
 
 const char* dabry_backend_name(void) { return DABRY_BACKEND::name(); }
 
+int dabry_host_register(void* p, size_t bytes) {
+    if (!p || bytes == 0) return DABRY_ERR_INVALID;
+    return DABRY_BACKEND::host_register(p, bytes) ? DABRY_OK : DABRY_ERR_CUDA;
+}
+
+int dabry_host_unregister(void* p) {
+    if (!p) return DABRY_ERR_INVALID;
+    return DABRY_BACKEND::host_unregister(p) ? DABRY_OK : DABRY_ERR_CUDA;
+}
+
 int dabry_create(const dabry_config* c, dabry_solver** out) {
     if (!c || !out) return DABRY_ERR_INVALID;
     *out = nullptr;

@@ -157,6 +157,23 @@ public:
         }
     }
 
+    // cudaHostRegister / cudaHostUnregister of a caller-owned array (dabry_host_register): portable, so that the
+    // pinning holds for every device of a multi-GPU process
+    static bool host_register(void* p, size_t bytes) {
+        const cudaError_t rc = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+        if (rc == cudaErrorHostMemoryAlreadyRegistered) {
+            cudaGetLastError();
+            return true;
+        }
+        if (rc != cudaSuccess) cudaGetLastError();
+        return rc == cudaSuccess;
+    }
+    static bool host_unregister(void* p) {
+        const cudaError_t rc = cudaHostUnregister(p);
+        if (rc != cudaSuccess) cudaGetLastError();
+        return rc == cudaSuccess;
+    }
+
     bool open(int device) {
         int count = 0;
         cudaError_t rc = cudaGetDeviceCount(&count);

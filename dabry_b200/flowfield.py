@@ -200,6 +200,23 @@ class DiscreteFF(FlowField):
             raise ValueError('Flowfield is steady')
         return np.linspace(self.t_start, self.t_end, self.values.shape[0])
 
+    def pin_memory(self):
+        """Page-lock `values` (and host-supplied `grad_values`) in place so that every upload of this field to a GPU is
+        one DMA at the PCIe rate instead of a driver-staged pageable copy (no reference counterpart; the arrays stay
+        ordinary numpy arrays).  Returns self."""
+        from dabry_b200 import _native as nat
+        if getattr(self, '_pins', None):
+            return self
+        self.values = np.ascontiguousarray(self.values, dtype=np.float64)
+        if not self.values.flags['WRITEABLE']:
+            self.values = self.values.copy()
+        pins = [nat.PinnedArray(self.values)]
+        if self.grad_values is not None and not self._grad_is_default:
+            self.grad_values = np.array(self.grad_values, dtype=np.float64, order='C', copy=None)
+            pins.append(nat.PinnedArray(self.grad_values))
+        self._pins = pins
+        return self
+
     @classmethod
     def from_npz(cls, filepath):
         """Flow file of docs/flow_format.md: arrays `values`, `bounds`, `coords` (flowfield.py:222-225)."""

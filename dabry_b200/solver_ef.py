@@ -225,6 +225,49 @@ class Site:
     __str__ = __repr__
 
 
+_ROOT_FAN_CACHE = {}
+
+
+def _root_fan(n, root_range, shard):
+    """[count][2] initial costates 1000 (cos, sin)(theta_i) of the local roots (solver_ef.py:465-467) with numpy's own
+    cos / sin.  The fan is a constant of (n, shard): large fans are computed by a few threads (numpy releases the GIL)
+    and the last one is kept, so that a sequence of solves with the same fan pays for it once."""
+    key = (n, root_range, shard)
+    hit = _ROOT_FAN_CACHE.get(key)
+    if hit is not None:
+        return hit
+    offset, count = (0, n) if root_range is None else root_range
+    j = np.arange(count)
+    if shard is not None:
+        _, world, block = shard
+        j = (j // block) * (world * block) + j % block
+    theta = np.linspace(0, 2 * np.pi, n, endpoint=False)[(offset + j) % n]  # the library validates the range
+    out = np.empty((count, 2))
+
+    def fill(lo, hi):
+        np.cos(theta[lo:hi], out=out[lo:hi, 0])
+        np.sin(theta[lo:hi], out=out[lo:hi, 1])
+        out[lo:hi] *= 1000
+
+    if count >= 1 << 16:
+        from concurrent.futures import ThreadPoolExecutor
+        import os
+        workers = max(1, min(8, os.cpu_count() or 1))
+        edges = np.linspace(0, count, workers + 1).astype(int)
+        with ThreadPoolExecutor(workers) as pool:
+            list(pool.map(lambda k: fill(edges[k], edges[k + 1]), range(workers)))
+    else:
+        fill(0, count)
+    if count >= 1 << 16:  # keep only the last large fan (16 B per root), page-locked for its uploads
+        _ROOT_FAN_CACHE.clear()
+        _ROOT_FAN_CACHE[key] = out
+        try:
+            _ROOT_FAN_CACHE['pin'] = nat.PinnedArray(out)
+        except Exception:
+            pass
+    return out
+
+
 class SolverEF(ABC):
     _ALL_MODES = ['time', 'energy']
     _VARIANT = nat.RESAMPLING
@@ -496,9 +539,7 @@ class SolverEFResampling(SolverEF):
         with numpy so that the device starts from the same bits as the reference."""
         if self.device_roots:
             return None
-        n = self.n_costate_sectors
-        theta = np.linspace(0, 2 * np.pi, n, endpoint=False)[self._ring_indices() % n]  # the library validates the range
-        return nat.f64(1000 * np.stack((np.cos(theta), np.sin(theta)), -1))
+        return _root_fan(self.n_costate_sectors, self.root_range, self.shard)
 
     def _ring_indices(self):
         """Ring (global) index of every local root, in slot order."""

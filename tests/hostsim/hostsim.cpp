@@ -30,6 +30,8 @@ namespace dabry {
 class SerialBackend {
 public:
     static const char* name() { return "hostsim-serial"; }
+    static bool host_register(void*, size_t) { return true; }
+    static bool host_unregister(void*) { return true; }
     bool open(int) { return true; }
     bool ok() const { return true; }
     const std::string& error() const { return err_; }

@@ -234,6 +234,49 @@ def test_chunked_free_arcs_are_bit_identical(hostsim, monkeypatch):
         assert np.array_equal(runs[0][1][n][0], runs[1][1][n][0]) and runs[0][1][n][1] == runs[1][1][n][1]
 
 
+def pinned_inputs_same_result():
+    """DiscreteFF.pin_memory (dabry_host_register) changes where the flow samples live, not what is computed: a solve
+    from the page-locked array equals the solve from the pageable one bit for bit, and the array stays plain numpy."""
+    from dabry_b200.solver_ef import SolverEFResampling
+    runs = []
+    for pin in (False, True):
+        pb, _ = _synthetic('era5_like', (5, 72, 37))
+        inner = pb.model.ff.ff
+        if pin:
+            before = inner.values.copy()
+            assert inner.pin_memory() is inner and inner.pin_memory() is inner  # idempotent
+            assert np.array_equal(inner.values, before)
+        s = SolverEFResampling(pb, 0.25, n_costate_sectors=64, max_depth=2)
+        s.solve()
+        runs.append((list(s.sites), np.stack([site.traj.states[-1] for site in s.sites.values()]), s.solution_cost))
+        s.close()
+    assert runs[0][0] == runs[1][0]
+    assert np.array_equal(runs[0][1], runs[1][1])
+    assert runs[0][2] == runs[1][2] or (np.isnan(runs[0][2]) and np.isnan(runs[1][2]))
+
+
+test_pinned_inputs_same_result_hostsim, test_pinned_inputs_same_result_gpu = _both(pinned_inputs_same_result)
+
+
+def test_root_fan_matches_numpy_and_shards():
+    """The threaded, cached root fan equals the reference's expression 1000 (cos, sin)(linspace) bit for bit
+    (solver_ef.py:465-467), and a block-cyclic shard is the matching subset of the ring."""
+    from dabry_b200.solver_ef import _root_fan
+    n = 1 << 17
+    theta = np.linspace(0, 2 * np.pi, n, endpoint=False)
+    ref = 1000 * np.stack((np.cos(theta), np.sin(theta)), -1)
+    full = _root_fan(n, None, None)
+    assert np.array_equal(full, ref)
+    assert _root_fan(n, None, None) is full  # cached
+    rank, world, block = 1, 4, 64
+    part = _root_fan(n, (rank * block, n // world), (rank, world, block))
+    j = np.arange(n // world)
+    assert np.array_equal(part, ref[rank * block + (j // block) * (world * block) + j % block])
+    small = _root_fan(30, None, None)
+    th = np.linspace(0, 2 * np.pi, 30, endpoint=False)
+    assert np.array_equal(small, 1000 * np.stack((np.cos(th), np.sin(th)), -1))
+
+
 def test_library_exports_every_declared_symbol():
     """Every function include/dabry_b200.h declares is exported by the built CUDA library and bound by ctypes (no
     compute call: this runs without a GPU)."""
