@@ -142,7 +142,7 @@ struct GhostInitPhase {  // ghost k = the ring root after the last root of local
 
 template <int FK, int METHOD, bool CHUNKED>
 struct FreeArcPhase {  // the hot kernel: one thread per extremal, free arc with events, `budget` RK steps per launch
-    static constexpr int kThreads = 128;
+    static constexpr int kThreads = DABRY_FREE_ARC_THREADS;
     static constexpr int kMinBlocks = DABRY_INTEGRATE_MIN_BLOCKS;  // register cap = 65536 / (128 * kMinBlocks)
     SiteStore S;
     const int32_t* list;  // null: sites [base, base + n)

@@ -59,11 +59,12 @@ struct IvpResult {
 // Events concept:  int count() const;  bool terminal(int e) const;  double value(int e, double t, const double* y) const;
 //                  void record(int e, double t_root);
 // Sink concept:    void emit(int j, double t, const double* y);     j indexes the un-sliced linspace
-template <int N, int METHOD, class Rhs, class Events, class Sink>
+template <int N, int METHOD, class KS = KRegisters<N>, class Rhs, class Events, class Sink>
 DABRY_HD void solve_ivp(const Rhs& rhs, Events& events, Sink& sink, double t0, double tf, const double* y0,
                         const EvalGrid& grid, double max_step, double rtol, double atol, IvpResult<N>& res,
-                        unsigned& n_attempts, IvpCarry<N>* carry = nullptr, int step_budget = 0) {
-    RkState<N> S;
+                        unsigned& n_attempts, IvpCarry<N>* carry = nullptr, int step_budget = 0, KS kstore = KS()) {
+    RkState<N, KS> S;
+    S.K = kstore;
     const int ne = events.count();
     double g[DABRY_MAX_EVENTS];
     int eval_i;
@@ -72,8 +73,8 @@ DABRY_HD void solve_ivp(const Rhs& rhs, Events& events, Sink& sink, double t0, d
         S.h_abs = carry->h_abs;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            S.y[i] = S.y_old[i] = carry->y[i];
-            S.f[i] = carry->f[i];
+            S.y[i] = S.K[7][i] = carry->y[i];
+            S.K[6][i] = carry->f[i];
         }
         for (int e = 0; e < ne; ++e) g[e] = carry->g[e];
         eval_i = carry->eval_i;
@@ -98,7 +99,7 @@ DABRY_HD void solve_ivp(const Rhs& rhs, Events& events, Sink& sink, double t0, d
 #pragma unroll
             for (int i = 0; i < N; ++i) {
                 carry->y[i] = S.y[i];
-                carry->f[i] = S.f[i];
+                carry->f[i] = S.K[6][i];
             }
             for (int e = 0; e < ne; ++e) carry->g[e] = g[e];
             res.status = IVP_RUNNING;

@@ -28,11 +28,37 @@ static const DormandPrince h_dp = DABRY_DP_INIT;
 #define DP(x) (h_dp.x)
 #endif
 
+// Where the stage values of a step live.  Rows 0..6 = K[0] = f(t_old, y_old) ... K[6] = f(t, y) (rk.py:61-69, after an
+// accepted step K[6] is the FSAL value the next step starts from), row 7 = y_old.
+//  * KRegisters: a plain array (registers / local memory) - host build, N = 2 arcs, every kernel but the hot one;
+//  * KShared (device): one 8-byte column per thread in shared memory, row stride = block size (conflict-free, constant
+//    offsets after unrolling).  The 32 doubles are live across the six non-inlined right-hand sides of a step; in
+//    registers they leave the right-hand side ~50 registers to work with (its 24 node loads then go out two or three at
+//    a time), in shared memory they cost one LDS each when a stage combination needs them.
 template <int N>
+struct KRegisters {
+    double v[8][N];
+    DABRY_HD double* operator[](int a) { return v[a]; }
+    DABRY_HD const double* operator[](int a) const { return v[a]; }
+};
+
+#if defined(__CUDACC__)
+template <int N, int THREADS>
+struct KShared {
+    double* base;  // &tile[threadIdx.x], tile = double[8 * N * THREADS] in shared memory
+    struct Row {
+        double* p;
+        __device__ double& operator[](int i) const { return p[i * THREADS]; }
+    };
+    __device__ Row operator[](int a) const { return Row{base + a * (N * THREADS)}; }
+};
+#endif
+
+template <int N, class KS = KRegisters<N>>
 struct RkState {
     double t, t_old, h_abs;
-    double y[N], y_old[N], f[N];
-    double K[7][N];  // K[0] = f(t_old, y_old) ... K[6] = f(t, y)   (rk.py:61-69)
+    double y[N];
+    KS K;
 };
 
 template <int N>
@@ -46,15 +72,24 @@ DABRY_HD double rms_norm_scaled(const double* v, const double* scale) {
     return sqrt(s) / sqrt((double) N);
 }
 
+template <int N, class KS>
+DABRY_HD void put_stage(KS& K, int stage, const double* k) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) K[stage][i] = k[i];
+}
+
 // RungeKutta.__init__ (rk.py:86-103): f0 and the empirical first step.  Costs 2 RHS evaluations.
-template <int N, class Rhs>
-DABRY_HD void rk_init(RkState<N>& S, const Rhs& rhs, double t0, const double* y0, double t_bound, double max_step,
+template <int N, class KS, class Rhs>
+DABRY_HD void rk_init(RkState<N, KS>& S, const Rhs& rhs, double t0, const double* y0, double t_bound, double max_step,
                       double rtol, double atol) {
     S.t = t0;
     S.t_old = t0;
 #pragma unroll
-    for (int i = 0; i < N; ++i) S.y[i] = S.y_old[i] = y0[i];
-    rhs(t0, S.y, S.f);
+    for (int i = 0; i < N; ++i) S.y[i] = S.K[7][i] = y0[i];
+    double f0[N];
+    rhs(t0, S.y, f0);
+#pragma unroll
+    for (int i = 0; i < N; ++i) S.K[6][i] = f0[i];
     // select_initial_step (common.py:68-134), direction = +1, error_estimator_order = 4
     const double interval = fabs(t_bound - t0);
     if (interval == 0.) {
@@ -65,15 +100,15 @@ DABRY_HD void rk_init(RkState<N>& S, const Rhs& rhs, double t0, const double* y0
 #pragma unroll
     for (int i = 0; i < N; ++i) scale[i] = atol + fabs(S.y[i]) * rtol;
     const double d0 = rms_norm_scaled<N>(S.y, scale);
-    const double d1 = rms_norm_scaled<N>(S.f, scale);
+    const double d1 = rms_norm_scaled<N>(f0, scale);
     double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
     h0 = dmin(h0, interval);
     double y1[N], f1[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) y1[i] = S.y[i] + h0 * S.f[i];
+    for (int i = 0; i < N; ++i) y1[i] = S.y[i] + h0 * f0[i];
     rhs(t0 + h0, y1, f1);
 #pragma unroll
-    for (int i = 0; i < N; ++i) f1[i] -= S.f[i];
+    for (int i = 0; i < N; ++i) f1[i] -= f0[i];
     const double d2 = rms_norm_scaled<N>(f1, scale) / h0;
     double h1;
     if (d1 <= 1e-15 && d2 <= 1e-15) h1 = dmax(1e-6, h0 * 1e-3);
@@ -83,8 +118,8 @@ DABRY_HD void rk_init(RkState<N>& S, const Rhs& rhs, double t0, const double* y0
 
 // One accepted step of RungeKutta._step_impl (rk.py:111-176).  Returns false on TOO_SMALL_STEP.
 // n_attempts is incremented once per attempted step (accepted or rejected): the metric's unit.
-template <int N, class Rhs>
-DABRY_HD bool rk_step(RkState<N>& S, const Rhs& rhs, double t_bound, double max_step, double rtol, double atol,
+template <int N, class KS, class Rhs>
+DABRY_HD bool rk_step(RkState<N, KS>& S, const Rhs& rhs, double t_bound, double max_step, double rtol, double atol,
                       unsigned& n_attempts) {
     const double t = S.t;
     // min_step = 10 ulp(t) (rk.py:119) only matters when the step is within a few ulps of t: 10 ulp(t) <= 4.5e-15 |t|,
@@ -96,7 +131,7 @@ DABRY_HD bool rk_step(RkState<N>& S, const Rhs& rhs, double t_bound, double max_
     bool rejected = false;
     double y_new[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) S.K[0][i] = S.f[i];
+    for (int i = 0; i < N; ++i) S.K[0][i] = S.K[6][i];  // FSAL: f(t, y) of the last accepted step
     for (;;) {
         if (!(h_abs > safe) && h_abs < 10. * ulp_above(t)) return false;
         double t_new = t + h_abs;
@@ -105,32 +140,38 @@ DABRY_HD bool rk_step(RkState<N>& S, const Rhs& rhs, double t_bound, double max_
         h_abs = fabs(h);
         ++n_attempts;
         // Dormand-Prince stages (rk.py:538-552)
-        double ys[N];
+        double ys[N], ks[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) ys[i] = S.y[i] + (DP(a21) * S.K[0][i]) * h;
-        rhs(t + DP(c2) * h, ys, S.K[1]);
+        rhs(t + DP(c2) * h, ys, ks);
+        put_stage<N>(S.K, 1, ks);
 #pragma unroll
         for (int i = 0; i < N; ++i) ys[i] = S.y[i] + (DP(a31) * S.K[0][i] + DP(a32) * S.K[1][i]) * h;
-        rhs(t + DP(c3) * h, ys, S.K[2]);
+        rhs(t + DP(c3) * h, ys, ks);
+        put_stage<N>(S.K, 2, ks);
 #pragma unroll
         for (int i = 0; i < N; ++i)
             ys[i] = S.y[i] + (DP(a41) * S.K[0][i] + DP(a42) * S.K[1][i] + DP(a43) * S.K[2][i]) * h;
-        rhs(t + DP(c4) * h, ys, S.K[3]);
+        rhs(t + DP(c4) * h, ys, ks);
+        put_stage<N>(S.K, 3, ks);
 #pragma unroll
         for (int i = 0; i < N; ++i)
             ys[i] = S.y[i] + (DP(a51) * S.K[0][i] + DP(a52) * S.K[1][i] + DP(a53) * S.K[2][i]
                               + DP(a54) * S.K[3][i]) * h;
-        rhs(t + DP(c5) * h, ys, S.K[4]);
+        rhs(t + DP(c5) * h, ys, ks);
+        put_stage<N>(S.K, 4, ks);
 #pragma unroll
         for (int i = 0; i < N; ++i)
             ys[i] = S.y[i] + (DP(a61) * S.K[0][i] + DP(a62) * S.K[1][i] + DP(a63) * S.K[2][i]
                               + DP(a64) * S.K[3][i] + DP(a65) * S.K[4][i]) * h;
-        rhs(t + h, ys, S.K[5]);
+        rhs(t + h, ys, ks);
+        put_stage<N>(S.K, 5, ks);
 #pragma unroll
         for (int i = 0; i < N; ++i)
             y_new[i] = S.y[i] + h * (DP(b1) * S.K[0][i] + DP(b3) * S.K[2][i] + DP(b4) * S.K[3][i]
                                      + DP(b5) * S.K[4][i] + DP(b6) * S.K[5][i]);
-        rhs(t + h, y_new, S.K[6]);
+        rhs(t + h, y_new, ks);
+        put_stage<N>(S.K, 6, ks);
         // error estimate (rk.py:105-109, :146-147)
         double err[N], scale[N];
 #pragma unroll
@@ -166,9 +207,8 @@ DABRY_HD bool rk_step(RkState<N>& S, const Rhs& rhs, double t_bound, double max_
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        S.y_old[i] = S.y[i];
+        S.K[7][i] = S.y[i];
         S.y[i] = y_new[i];
-        S.f[i] = S.K[6][i];
     }
     S.h_abs = h_abs;
     return true;
@@ -182,13 +222,13 @@ struct Dense {
     double Q[N][4];
 };
 
-template <int N>
-DABRY_HD void rk_dense(const RkState<N>& S, Dense<N>& D) {
+template <int N, class KS>
+DABRY_HD void rk_dense(const RkState<N, KS>& S, Dense<N>& D) {
     D.t_old = S.t_old;
     D.h = S.t - S.t_old;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        D.y_old[i] = S.y_old[i];
+        D.y_old[i] = S.K[7][i];
         const double k0 = S.K[0][i], k2 = S.K[2][i], k3 = S.K[3][i], k4 = S.K[4][i], k5 = S.K[5][i], k6 = S.K[6][i];
         D.Q[i][0] = k0;
         D.Q[i][1] = DP(p11) * k0 + DP(p13) * k2 + DP(p14) * k3 + DP(p15) * k4 + DP(p16) * k5 + DP(p17) * k6;
@@ -213,18 +253,20 @@ DABRY_HD void dense_eval(const Dense<N>& D, double t, double* y) {
 // scipy OdeSolver subclass, so the driver semantics (events, t_eval) are scipy's in both.
 enum Integrator : int32_t { METHOD_DOPRI5 = 0, METHOD_RK4 = 1 };
 
-template <int N, class Rhs>
-DABRY_HD void rk4_init(RkState<N>& S, const Rhs& rhs, double t0, const double* y0, double max_step) {
+template <int N, class KS, class Rhs>
+DABRY_HD void rk4_init(RkState<N, KS>& S, const Rhs& rhs, double t0, const double* y0, double max_step) {
     S.t = t0;
     S.t_old = t0;
 #pragma unroll
-    for (int i = 0; i < N; ++i) S.y[i] = S.y_old[i] = y0[i];
-    rhs(t0, S.y, S.f);
+    for (int i = 0; i < N; ++i) S.y[i] = S.K[7][i] = y0[i];
+    double f0[N];
+    rhs(t0, S.y, f0);
+    put_stage<N>(S.K, 6, f0);
     S.h_abs = max_step;
 }
 
-template <int N, class Rhs>
-DABRY_HD bool rk4_step(RkState<N>& S, const Rhs& rhs, double t_bound, double max_step, unsigned& n_attempts) {
+template <int N, class KS, class Rhs>
+DABRY_HD bool rk4_step(RkState<N, KS>& S, const Rhs& rhs, double t_bound, double max_step, unsigned& n_attempts) {
     const double t = S.t;
     double t_new = t + max_step;
     if (t_new - t_bound > 0.) t_new = t_bound;
@@ -233,7 +275,7 @@ DABRY_HD bool rk4_step(RkState<N>& S, const Rhs& rhs, double t_bound, double max
     double ys[N], k2[N], k3[N], k4[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        S.K[0][i] = S.f[i];
+        S.K[0][i] = S.K[6][i];
         ys[i] = S.y[i] + (0.5 * h) * S.K[0][i];
     }
     rhs(t + 0.5 * h, ys, k2);
@@ -245,27 +287,27 @@ DABRY_HD bool rk4_step(RkState<N>& S, const Rhs& rhs, double t_bound, double max
     rhs(t_new, ys, k4);
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        S.y_old[i] = S.y[i];
+        S.K[7][i] = S.y[i];
         S.y[i] = S.y[i] + (h / 6.) * (((S.K[0][i] + 2. * k2[i]) + 2. * k3[i]) + k4[i]);
     }
-    rhs(t_new, S.y, S.f);
-#pragma unroll
-    for (int i = 0; i < N; ++i) S.K[6][i] = S.f[i];
+    double f1[N];
+    rhs(t_new, S.y, f1);
+    put_stage<N>(S.K, 6, f1);
     S.t_old = t;
     S.t = t_new;
     return true;
 }
 
 // cubic Hermite interpolant in the polynomial form of Dense: y(t_old + x h) = y_old + h (Q0 x + Q1 x^2 + Q2 x^3)
-template <int N>
-DABRY_HD void rk4_dense(const RkState<N>& S, Dense<N>& D) {
+template <int N, class KS>
+DABRY_HD void rk4_dense(const RkState<N, KS>& S, Dense<N>& D) {
     D.t_old = S.t_old;
     D.h = S.t - S.t_old;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        D.y_old[i] = S.y_old[i];
+        D.y_old[i] = S.K[7][i];
         const double f0 = S.K[0][i], f1 = S.K[6][i];
-        const double slope = (S.y[i] - S.y_old[i]) / D.h;
+        const double slope = (S.y[i] - D.y_old[i]) / D.h;
         D.Q[i][0] = f0;
         D.Q[i][1] = (3. * slope - 2. * f0) - f1;
         D.Q[i][2] = (f0 + f1) - 2. * slope;

@@ -14,6 +14,13 @@
 #include "ivp.cuh"
 #include "model.cuh"
 
+// 1: Runge-Kutta stage values of the hot kernel in shared memory instead of registers / local memory.  Measured equal
+// (25.9 vs 25.5 ms, DESIGN.md 6: the kernel is bound by L1 data-pipe wavefronts, and an LDS costs what an LDL costs)
+#ifndef DABRY_K_IN_SHARED
+#define DABRY_K_IN_SHARED 0
+#endif
+#define DABRY_FREE_ARC_THREADS 128  // block size of the free-arc kernel (FreeArcPhase::kThreads)
+
 namespace dabry {
 
 struct Sample {  // 32-byte record: one aligned sector per grid sample
@@ -238,8 +245,16 @@ DABRY_HD void site_free_arc(const ProblemDev& P, const SiteStore& S, int s, int 
     FreeEvents ev{P, S, s};
     FreeSink sink{S, s, idx0};
     IvpResult<4> res;
+#if defined(__CUDA_ARCH__) && DABRY_K_IN_SHARED
+    // the hot kernel keeps the stage values of the step in shared memory (rk45.cuh KShared): 32 KB per block
+    __shared__ double k_tile[8 * 4 * DABRY_FREE_ARC_THREADS];
+    solve_ivp<4, METHOD, KShared<4, DABRY_FREE_ARC_THREADS>>(
+        rhs, ev, sink, grid.at(0), grid.at(n - 1), y0, grid, P.max_step, P.rtol, P.atol, res, n_attempts,
+        CHUNKED ? &carry : nullptr, CHUNKED ? step_budget : 0, KShared<4, DABRY_FREE_ARC_THREADS>{k_tile + threadIdx.x});
+#else
     solve_ivp<4, METHOD>(rhs, ev, sink, grid.at(0), grid.at(n - 1), y0, grid, P.max_step, P.rtol, P.atol, res, n_attempts,
                          CHUNKED ? &carry : nullptr, CHUNKED ? step_budget : 0);
+#endif
     S.n_samples[s] += res.n_emitted;
     if (CHUNKED && res.status == IVP_RUNNING) {
         S.flags[s] |= SITE_RUNNING;

@@ -13,7 +13,16 @@ WANT = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'la
         'smsp__inst_executed.sum', 'smsp__thread_inst_executed_per_inst_executed.ratio',
         'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct', 'lts__t_bytes.sum', 'l1tex__t_bytes.sum',
         'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
-        'smsp__inst_executed_op_local_ld.sum', 'smsp__inst_executed_op_local_st.sum']
+        'smsp__inst_executed_op_local_ld.sum', 'smsp__inst_executed_op_local_st.sum',
+        # the L1 data stage: every 128 B delivered to the register file is one wavefront, broadcast or not
+        'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed', 'l1tex__data_pipe_lsu_wavefronts.sum',
+        'l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_elapsed', 'l1tex__throughput.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_requests_pipe_lsu_mem_local_op_ld.sum',
+        'l1tex__t_requests_pipe_lsu_mem_local_op_st.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_st.sum',
+        'l1tex__t_sector_pipe_lsu_mem_global_op_ld_hit_rate.pct', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active',
+        'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio']
 
 
 def main(rep):
