@@ -409,13 +409,19 @@ def main():
         t0 = time.perf_counter()
         rk_sum, d2h = 0, 0
         n_e2e = max(1, min(args.steps, 3))
+        step_ms, step_calls = [], []
         for _ in range(n_e2e):
+            nat.CALL_TIMES = {}
+            t1 = time.perf_counter()
             cost_e2e, rk, d2h = e2e_step()
             rk_sum += rk
+            step_ms.append(round(1e3 * (time.perf_counter() - t1), 2))
+            step_calls.append({k[6:]: round(1e3 * v, 2) for k, v in nat.CALL_TIMES.items() if v > 2e-4})
+        nat.CALL_TIMES = None
         barrier()
         e2e_s = reduce_max(time.perf_counter() - t0)
         e2e = {'value': reduce_sum(float(rk_sum)) / e2e_s, 'unit': 'steps/s', 'h2d_bytes_per_step': h2d,
-               'd2h_bytes_per_step': int(d2h), 'steps': n_e2e, 'ms_per_step': 1e3 * e2e_s / n_e2e,
+               'd2h_bytes_per_step': int(d2h), 'steps': n_e2e, 'ms_per_step': 1e3 * e2e_s / n_e2e, 'ms_each_step_rank0': step_ms, 'native_ms_slowest_step_rank0': step_calls[int(np.argmax(step_ms))],
                'arrival_cost': None if np.isnan(cost_e2e) else cost_e2e}
 
     # ---- CPU baseline (rank 0, N = 1) ----

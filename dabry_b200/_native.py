@@ -6,6 +6,7 @@ fallback.  `use_library(path)` exists for the CPU-only test tier, which loads te
 (the same device headers compiled by g++) to exercise the host logic without a GPU; nothing in this package calls it.
 """
 import ctypes as C
+import time
 import os
 
 import numpy as np
@@ -90,6 +91,7 @@ SIGNATURES = {
     'dabry_backend_name': (C.c_char_p, []),
     'dabry_host_register': (C.c_int, [C.c_void_p, C.c_size_t]),
     'dabry_host_unregister': (C.c_int, [C.c_void_p]),
+    'dabry_release_cached_memory': (C.c_int, [C.c_int32]),
     'dabry_set_flow_grid': (C.c_int, [_H, c_double_p, c_double_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                       c_double_p, c_double_p, C.POINTER(Wrapper)]),
     'dabry_set_flow_program': (C.c_int, [_H, C.POINTER(Leaf), C.c_int32, c_double_p, C.c_int64, C.POINTER(Wrapper)]),
@@ -171,6 +173,23 @@ def f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
+CALL_TIMES = None  # diagnostic: set to a dict to accumulate the wall time of every native call by entry point
+
+
+def _now():
+    return time.perf_counter() if CALL_TIMES is not None else 0.
+
+
+def _note(name, t0):
+    if CALL_TIMES is not None:
+        CALL_TIMES[name] = CALL_TIMES.get(name, 0.) + time.perf_counter() - t0
+
+
+def release_cached_memory(device=0):
+    """Give the device blocks parked by closed solvers back to the driver (dabry_release_cached_memory)."""
+    return library().dabry_release_cached_memory(device)
+
+
 class PinnedArray:
     """Page-locks a C-contiguous numpy array in place (dabry_host_register) for as long as this object lives, so that
     its H2D copies run at the PCIe rate.  The array itself is untouched and stays usable as plain numpy."""
@@ -205,7 +224,9 @@ class Handle:
         self._lib = library()
         self._h = _H()
         self._keep = keepalive
+        t0 = _now()
         rc = self._lib.dabry_create(C.byref(config), C.byref(self._h))
+        _note('dabry_create', t0)
         if rc != 0:
             msg = self._lib.dabry_last_error(None)
             raise NativeError(rc, msg.decode() if msg else 'dabry_create failed')
@@ -213,7 +234,9 @@ class Handle:
 
     def close(self):
         if getattr(self, '_h', None):
+            t0 = _now()
             self._lib.dabry_destroy(self._h)
+            _note('dabry_destroy', t0)
             self._h = None
 
     def __del__(self):
@@ -223,7 +246,9 @@ class Handle:
             pass
 
     def call(self, name, *args):
+        t0 = _now()
         rc = getattr(self._lib, name)(self._h, *args)
+        _note(name, t0)
         if rc != 0:
             msg = self._lib.dabry_last_error(self._h)
             raise NativeError(rc, msg.decode() if msg else name)

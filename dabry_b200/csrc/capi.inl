@@ -31,6 +31,10 @@ int dabry_host_unregister(void* p) {
     return DABRY_BACKEND::host_unregister(p) ? DABRY_OK : DABRY_ERR_CUDA;
 }
 
+int dabry_release_cached_memory(int32_t device) {
+    return DABRY_BACKEND::release_cached(device) ? DABRY_OK : DABRY_ERR_INVALID;
+}
+
 int dabry_create(const dabry_config* c, dabry_solver** out) {
     if (!c || !out) return DABRY_ERR_INVALID;
     *out = nullptr;
@@ -48,13 +52,21 @@ int dabry_create(const dabry_config* c, dabry_solver** out) {
         g_create_error = "unknown dtype / integrator";
         return DABRY_ERR_UNSUPPORTED;
     }
+    // DABRY_B200_DEBUG_TIMING=1: host wall time of the two halves of dabry_create on stderr (diagnostic)
+    const bool timing = getenv("DABRY_B200_DEBUG_TIMING") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     dabry::Engine<DABRY_BACKEND>* e = new dabry::Engine<DABRY_BACKEND>(*c);
     if (!e->be.open(c->device)) {
         g_create_error = e->be.error();
         delete e;
         return DABRY_ERR_NO_DEVICE;
     }
+    const auto t1 = std::chrono::steady_clock::now();
     const int rc = e->init();
+    if (timing)
+        fprintf(stderr, "dabry_create: open %.2f ms, init %.2f ms\n",
+                std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
     if (rc != DABRY_OK) {
         g_create_error = e->err;
         delete e;

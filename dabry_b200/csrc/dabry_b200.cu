@@ -4,6 +4,11 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 
+#include <chrono>
+#include <map>
+#include <mutex>
+#include <unordered_map>
+
 #include "engine.cuh"
 
 namespace dabry {
@@ -141,6 +146,65 @@ __global__ void __launch_bounds__(256) first_equal_kernel(const double* __restri
     if ((threadIdx.x & 31) == 0 && best != ~0ull) atomicMin(out_index, best);
 }
 
+// ---- process-wide cache of large device blocks --------------------------------------------------------------------
+// One free list per device.  give(): a handle parks a block together with an event recorded on its stream after the
+// block's last use.  take(): the smallest parked block that fits and is at most 25 % larger; the taker makes its stream
+// wait on the event.  The cache holds at most kMaxBytes per device (DABRY_B200_CACHE_MB overrides; 0 disables).
+class DeviceBlockCache {
+public:
+    static constexpr size_t kMinBytes = (size_t) 1 << 20;
+    static DeviceBlockCache& instance() {
+        static DeviceBlockCache cache;
+        return cache;
+    }
+    void* take(int device, size_t bytes, size_t* got, cudaEvent_t* ready) {
+        std::lock_guard<std::mutex> lock(mutex_);
+        std::vector<Block>& v = blocks_[device];
+        int best = -1;
+        for (int i = 0; i < (int) v.size(); ++i)
+            if (v[i].bytes >= bytes && v[i].bytes <= bytes + bytes / 4 && (best < 0 || v[i].bytes < v[best].bytes)) best = i;
+        if (best < 0) return nullptr;
+        const Block b = v[best];
+        v.erase(v.begin() + best);
+        held_[device] -= b.bytes;
+        *got = b.bytes;
+        *ready = b.ready;
+        return b.p;
+    }
+    bool give(int device, void* p, size_t bytes, cudaEvent_t ready) {
+        std::lock_guard<std::mutex> lock(mutex_);
+        if (held_[device] + bytes > limit_) return false;
+        blocks_[device].push_back(Block{p, bytes, ready});
+        held_[device] += bytes;
+        return true;
+    }
+    void trim(int device, cudaStream_t stream) {  // hand every parked block of the device back to the pool
+        std::lock_guard<std::mutex> lock(mutex_);
+        for (const Block& b : blocks_[device]) {
+            cudaStreamWaitEvent(stream, b.ready, 0);
+            cudaEventDestroy(b.ready);
+            cudaFreeAsync(b.p, stream);
+        }
+        blocks_[device].clear();
+        held_[device] = 0;
+    }
+
+private:
+    struct Block {
+        void* p;
+        size_t bytes;
+        cudaEvent_t ready;
+    };
+    DeviceBlockCache() {
+        limit_ = (size_t) 96 << 30;
+        if (const char* env = getenv("DABRY_B200_CACHE_MB")) limit_ = (size_t) strtoull(env, nullptr, 10) << 20;
+    }
+    std::mutex mutex_;
+    std::map<int, std::vector<Block>> blocks_;
+    std::map<int, size_t> held_;
+    size_t limit_;
+};
+
 // ---- backend ------------------------------------------------------------------------------------------------
 class CudaBackend {
 public:
@@ -151,10 +215,29 @@ public:
             cudaStreamSynchronize(stream_);
             for (cudaEvent_t e : {ev0_, ev1_, tot0_, tot1_})
                 if (e) cudaEventDestroy(e);
-            if (d_small_) cudaFree(d_small_);
-            if (d_block_sum_) cudaFree(d_block_sum_);
+            if (d_small_) cudaFreeAsync(d_small_, stream_);
+            if (d_block_sum_) cudaFreeAsync(d_block_sum_, stream_);
+            cudaStreamSynchronize(stream_);
             cudaStreamDestroy(stream_);
         }
+    }
+
+    // dabry_release_cached_memory: parked blocks of one device back to the driver
+    static bool release_cached(int device) {
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+            cudaGetLastError();
+            return false;
+        }
+        int before = 0;
+        cudaGetDevice(&before);
+        cudaSetDevice(device);
+        DeviceBlockCache::instance().trim(device, nullptr);
+        cudaStreamSynchronize(nullptr);
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+        cudaSetDevice(before);
+        return true;
     }
 
     // cudaHostRegister / cudaHostUnregister of a caller-owned array (dabry_host_register): portable, so that the
@@ -186,26 +269,31 @@ public:
             err_ = "CUDA device ordinal out of range";
             return false;
         }
-        cudaDeviceProp prop;
-        if (!chk(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) return false;
-        if (prop.major != 10) {
-            err_ = std::string("device '") + prop.name + "' is not sm_100: this library ships sm_100a code only";
+        // two attribute reads instead of cudaGetDeviceProperties, which walks the whole property table (1 - 90 ms
+        // measured per call on a busy host; a handle is opened for every solve)
+        int major = 0, sms = 0;
+        if (!chk(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device), "cudaDeviceGetAttribute") ||
+            !chk(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device), "cudaDeviceGetAttribute"))
+            return false;
+        if (major != 10) {
+            err_ = "device " + std::to_string(device) + " is compute capability " + std::to_string(major) +
+                   ".x, not sm_100: this library ships sm_100a code only";
             return false;
         }
         device_ = device;
-        sm_count_ = prop.multiProcessorCount;
+        sm_count_ = sms;
         if (!chk(cudaSetDevice(device), "cudaSetDevice")) return false;
         if (!chk(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
         cudaEventCreate(&ev0_);
         cudaEventCreate(&ev1_);
         cudaEventCreate(&tot0_);
         cudaEventCreate(&tot1_);
-        if (!chk(cudaMalloc(&d_small_, 64), "cudaMalloc")) return false;
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
             unsigned long long keep = ~0ull;
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
+        if (!chk(cudaMallocAsync(&d_small_, 64, stream_), "cudaMallocAsync")) return false;
         cudaGetLastError();
         return true;
     }
@@ -215,21 +303,63 @@ public:
     uint64_t launches() const { return launches_; }
     cudaStream_t stream() const { return stream_; }
 
-    // Stream-ordered allocations from the device's default memory pool with an unbounded release threshold: freed
-    // blocks stay cached in the pool, so a second solver of the same shape (the usual pattern: one handle per
-    // solve() call) does not pay cudaMalloc / cudaFree again (measured 13 - 300 ms per solve for 10 GB of site store).
+    // Device memory.  Fresh blocks come stream-ordered from the device's default memory pool (unbounded release
+    // threshold).  Blocks of 1 MB and more are NOT given back when a solver lets go of them: they go to a process-wide
+    // per-device cache (DeviceBlockCache below) and the next solver of the same shape - the usual pattern is one handle
+    // per solve() call - takes them from there.  Measured without it: dabry_create / dabry_destroy cost 3 - 40 ms per
+    // solve with outliers of 170 - 420 ms when the driver trims and refills the pool (10 GB of site store).
     void* alloc(size_t bytes) {
         if (bytes == 0) bytes = 8;
         void* p = nullptr;
+        if (bytes >= DeviceBlockCache::kMinBytes) {
+            cudaEvent_t ready = nullptr;
+            size_t got = 0;
+            p = DeviceBlockCache::instance().take(device_, bytes, &got, &ready);
+            if (p) {
+                if (ready) {  // the block's last use was ordered on another handle's stream
+                    cudaStreamWaitEvent(stream_, ready, 0);
+                    cudaEventDestroy(ready);
+                }
+                live_[p] = got;
+                return p;
+            }
+        }
         if (cudaMallocAsync(&p, bytes, stream_) != cudaSuccess) {
             cudaGetLastError();
-            return nullptr;
+            // out of memory: give the cached blocks of this device back and try once more
+            DeviceBlockCache::instance().trim(device_, stream_);
+            cudaStreamSynchronize(stream_);
+            if (cudaMallocAsync(&p, bytes, stream_) != cudaSuccess) {
+                cudaGetLastError();
+                return nullptr;
+            }
         }
+        if (bytes >= DeviceBlockCache::kMinBytes) live_[p] = bytes;
         return p;
     }
     template <class T>
-    void free(T* p) {
-        if (p) cudaFreeAsync((void*) p, stream_);
+    void free(T* ptr) {
+        void* p = (void*) ptr;
+        if (!p) return;
+        auto it = live_.find(p);
+        if (it == live_.end()) {
+            cudaFreeAsync(p, stream_);
+            return;
+        }
+        const size_t bytes = it->second;
+        live_.erase(it);
+        cudaEvent_t ready = nullptr;
+        if (cudaEventCreateWithFlags(&ready, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventRecord(ready, stream_) != cudaSuccess) {
+            cudaGetLastError();
+            if (ready) cudaEventDestroy(ready);
+            cudaFreeAsync(p, stream_);
+            return;
+        }
+        if (!DeviceBlockCache::instance().give(device_, p, bytes, ready)) {
+            cudaEventDestroy(ready);
+            cudaFreeAsync(p, stream_);
+        }
     }
     void upload(void* d, const void* h, size_t bytes) {
         chk(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, stream_), "H2D copy");
@@ -265,9 +395,9 @@ public:
         if (n <= 0 || !ok()) return 0;
         const int64_t blocks = (n + kScanBlock - 1) / kScanBlock;
         if (blocks > block_sum_cap_) {
-            if (d_block_sum_) cudaFree(d_block_sum_);
+            if (d_block_sum_) cudaFreeAsync(d_block_sum_, stream_);
             block_sum_cap_ = blocks + blocks / 2 + 64;
-            if (!chk(cudaMalloc(&d_block_sum_, sizeof(int32_t) * block_sum_cap_), "cudaMalloc")) return 0;
+            if (!chk(cudaMallocAsync(&d_block_sum_, sizeof(int32_t) * block_sum_cap_, stream_), "cudaMallocAsync")) return 0;
         }
         scan_pass1<<<(unsigned) blocks, kScanBlock, 0, stream_>>>(request, n, offset, d_block_sum_);
         scan_pass2<<<1, kScanBlock, 0, stream_>>>(d_block_sum_, blocks, (int64_t*) d_small_);
@@ -332,6 +462,7 @@ private:
     }
     int device_ = 0, sm_count_ = 148;
     cudaStream_t stream_ = nullptr;
+    std::unordered_map<void*, size_t> live_;  // cacheable blocks this handle holds -> their real size
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr, tot0_ = nullptr, tot1_ = nullptr;
     void* d_small_ = nullptr;
     int32_t* d_block_sum_ = nullptr;

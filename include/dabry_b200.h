@@ -171,6 +171,10 @@ const char* dabry_backend_name(void);                /* "cuda-sm100a" for the pr
  * counterpart (numpy arrays are the reference's only storage, flowfield.py:183-214). */
 int dabry_host_register(void* p, size_t bytes);
 int dabry_host_unregister(void* p);
+/* The library parks the large device blocks of a destroyed solver in a per-device cache so that the next solver of the
+ * same shape starts without allocating (one handle per solve() is the reference's usage pattern).  This gives them back
+ * to the driver.  DABRY_B200_CACHE_MB in the environment bounds the cache (0 disables it). */
+int dabry_release_cached_memory(int32_t device);
 
 /* ---- problem ------------------------------------------------------------------------------------------- */
 /* DiscreteFF (flowfield.py:178-214) seen through WrapperFF (518-544).  values: C-order (nt, nx, ny, 2), or

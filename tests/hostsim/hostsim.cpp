@@ -32,6 +32,7 @@ public:
     static const char* name() { return "hostsim-serial"; }
     static bool host_register(void*, size_t) { return true; }
     static bool host_unregister(void*) { return true; }
+    static bool release_cached(int) { return true; }
     bool open(int) { return true; }
     bool ok() const { return true; }
     const std::string& error() const { return err_; }
