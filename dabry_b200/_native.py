@@ -121,6 +121,10 @@ SIGNATURES = {
     'dabry_boundary_count': (C.c_int, [_H, C.POINTER(C.c_int64)]),
     'dabry_export_boundary': (C.c_int, [_H, c_double_p]),
     'dabry_import_boundary': (C.c_int, [_H, c_double_p]),
+    'dabry_export_boundary_device': (C.c_int, [_H, C.c_void_p]),
+    'dabry_import_boundary_device': (C.c_int, [_H, C.c_void_p]),
+    'dabry_get_cost_map_device': (C.c_int, [_H, C.c_int32, C.c_void_p]),
+    'dabry_set_cost_map_device': (C.c_int, [_H, C.c_void_p]),
     'dabry_eval_rhs': (C.c_int, [_H, C.c_int64, c_double_p, c_double_p, c_double_p]),
     'dabry_eval_flow': (C.c_int, [_H, C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p]),
 }

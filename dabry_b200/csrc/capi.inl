@@ -241,6 +241,30 @@ int dabry_import_boundary(dabry_solver* h, const double* packed) {
     return E.import_boundary(packed);
 }
 
+int dabry_export_boundary_device(dabry_solver* h, double* d_packed) {
+    DABRY_GUARD(h);
+    if (!d_packed) return DABRY_ERR_INVALID;
+    return E.export_boundary(d_packed, true);
+}
+
+int dabry_import_boundary_device(dabry_solver* h, const double* d_packed) {
+    DABRY_GUARD(h);
+    if (!d_packed) return DABRY_ERR_INVALID;
+    return E.import_boundary(d_packed, true);
+}
+
+int dabry_get_cost_map_device(dabry_solver* h, int32_t full, double* d_out) {
+    DABRY_GUARD(h);
+    if (!d_out) return DABRY_ERR_INVALID;
+    return E.get_cost_map(full, d_out, true);
+}
+
+int dabry_set_cost_map_device(dabry_solver* h, const double* d_map) {
+    DABRY_GUARD(h);
+    if (!d_map) return DABRY_ERR_INVALID;
+    return E.set_cost_map(d_map, true);
+}
+
 int dabry_eval_rhs(dabry_solver* h, int64_t n, const double* t, const double* y, double* dy) {
     DABRY_GUARD(h);
     if (n <= 0) return DABRY_OK;

@@ -808,8 +808,16 @@ public:
         return check();
     }
 
-    int set_cost_map(const double* map) {
-        be.upload(d_map, map, sizeof(double) * C.cm_nx * C.cm_ny);
+    // on_device: `map` is a device pointer on this handle's device (an NCCL buffer of the caller, synchronised by the
+    // caller before the call); the copy is ordered on the handle's stream and complete on return
+    int set_cost_map(const double* map, bool on_device = false) {
+        const size_t bytes = sizeof(double) * C.cm_nx * C.cm_ny;
+        if (on_device) {
+            be.copy2d(d_map, bytes, map, bytes, bytes, 1);
+            be.sync();
+        } else {
+            be.upload(d_map, map, bytes);
+        }
         return check();
     }
 
@@ -920,12 +928,18 @@ public:
         return check();
     }
 
-    int get_cost_map(int full, double* out) {
+    int get_cost_map(int full, double* out, bool on_device = false) {
         bind();
         if (full) {
             if (int rc = build_cost_map(0, cfg.n_time - 1, 1, 0, 0, 0)) return rc;
         }
-        be.download(out, d_map, sizeof(double) * C.cm_nx * C.cm_ny);
+        const size_t bytes = sizeof(double) * C.cm_nx * C.cm_ny;
+        if (on_device) {
+            be.copy2d(out, bytes, d_map, bytes, bytes, 1);
+            be.sync();
+        } else {
+            be.download(out, d_map, bytes);
+        }
         return check();
     }
 
@@ -951,23 +965,27 @@ public:
     // one packet per local block: export = the FIRST root of every block, import = the ghost of every block
     int64_t boundary_doubles() const { return (int64_t) cfg.n_time * 7 + DABRY_BOUNDARY_HEADER; }
     int64_t boundary_count() const { return n_blocks; }
-    int export_boundary(double* packed) {
+    // on_device: `packed` is a device buffer of the caller on this handle's device (the tensor NCCL sends / received
+    // into); the packets are written / read in place, no host staging.  The call returns with the stream drained.
+    int export_boundary(double* packed, bool on_device = false) {
         const int64_t n = boundary_doubles() * n_blocks;
-        double* d = (double*) scratch(sizeof(double) * n);
+        double* d = on_device ? packed : (double*) scratch(sizeof(double) * n);
         if (!d) return fail(DABRY_ERR_CAPACITY, "out of device memory");
         BoundaryPhase ph{S, 0, cfg.n_time, cfg.root_count, shard_b, boundary_doubles(), d};
         be.launch(n_blocks * cfg.n_time, ph);
-        be.download(packed, d, sizeof(double) * n);
+        if (on_device) be.sync();
+        else be.download(packed, d, sizeof(double) * n);
         return check();
     }
-    int import_boundary(const double* packed) {
+    int import_boundary(const double* packed, bool on_device = false) {
         if (!has_ghost) return fail(DABRY_ERR_INVALID, "this handle owns the whole ring: no ghost site");
         const int64_t n = boundary_doubles() * n_blocks;
-        double* d = (double*) scratch(sizeof(double) * n);
+        double* d = on_device ? const_cast<double*>(packed) : (double*) scratch(sizeof(double) * n);
         if (!d) return fail(DABRY_ERR_CAPACITY, "out of device memory");
-        be.upload(d, packed, sizeof(double) * n);
+        if (!on_device) be.upload(d, packed, sizeof(double) * n);
         BoundaryPhase ph{S, 1, cfg.n_time, cfg.root_count, shard_b, boundary_doubles(), d};
         be.launch(n_blocks * cfg.n_time, ph);
+        if (on_device) be.sync();
         return check();
     }
 

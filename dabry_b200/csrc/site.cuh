@@ -185,8 +185,7 @@ struct FreeSink {
     DABRY_HD void emit(int j, double t, const double* y) {
         const int64_t o = S.at(site, slot0 + j);
         S.xp[o] = Sample{y[0], y[1], y[2], y[3]};
-        S.ctrl[o] = Control{quiet_nan(), quiet_nan()};
-        S.tt[o] = t;
+        S.tt[o] = t;  // the control stays NaN (free arc, solver_ef.py:500): the store is pre-filled, no write here
     }
 };
 

@@ -55,26 +55,49 @@ class ShardedResampling:
             t = t.cuda(self.solver.device)
         return t
 
+    def _on_device(self):
+        return self.dist.get_backend(self.group) == 'nccl'
+
+    def _buffer(self, name, shape):
+        """Persistent exchange buffer: a CUDA tensor on the solver's device under NCCL (the library reads and writes it
+        in place through the *_device entry points), a CPU tensor under gloo (tests/hostsim: 'device' memory is host
+        memory there, so the same entry points apply)."""
+        import torch
+        bufs = self.__dict__.setdefault('_bufs', {})
+        t = bufs.get(name)
+        if t is None or tuple(t.shape) != tuple(shape):
+            device = torch.device('cuda', self.solver.device) if self._on_device() else torch.device('cpu')
+            t = bufs[name] = torch.empty(shape, dtype=torch.float64, device=device)
+        return t
+
+    def _sync_collective(self):
+        """NCCL work is ordered on torch's stream, the library's on its own: drain torch's before handing a buffer over."""
+        if self._on_device():
+            import torch
+            torch.cuda.current_stream(self.solver.device).synchronize()
+
     def _exchange_boundary(self, handle):
-        """first root of every block of rank r -> ghost of the preceding block, which lives on rank r - 1 (ring)."""
+        """first root of every block of rank r -> ghost of the preceding block, which lives on rank r - 1 (ring).
+        Device to device: the packets are written into the NCCL send buffer by the export kernel and read from the
+        receive buffer by the import kernel (dabry_export/import_boundary_device); nothing is staged on the host."""
         import ctypes as C
+        import torch
         size, count = C.c_int64(), C.c_int64()
         handle.call('dabry_boundary_doubles', C.byref(size))
         handle.call('dabry_boundary_count', C.byref(count))
-        send = np.empty((count.value, size.value))
-        handle.call('dabry_export_boundary', nat.dptr(send))
-        t_send, t_recv = self._tensor(send), self._tensor(np.empty_like(send))
+        t_send = self._buffer('send', (count.value, size.value))
+        t_recv = self._buffer('recv', (count.value, size.value))
+        handle.call('dabry_export_boundary_device', C.c_void_p(t_send.data_ptr()))
         dist = self.dist
         ops = [dist.P2POp(dist.isend, t_send, (self.rank - 1) % self.world, self.group),
                dist.P2POp(dist.irecv, t_recv, (self.rank + 1) % self.world, self.group)]
         for req in dist.batch_isend_irecv(ops):
             req.wait()
-        recv = t_recv.cpu().numpy()
         # block k of rank r is followed by block k of rank r + 1, except on the last rank: by block k + 1 of rank 0
         if self.rank == self.world - 1:
-            recv = np.roll(recv, -1, axis=0)
-        recv = np.ascontiguousarray(recv)
-        handle.call('dabry_import_boundary', nat.dptr(recv))
+            t_recv = torch.roll(t_recv, -1, dims=0).contiguous()
+        self._sync_collective()
+        handle.call('dabry_import_boundary_device', C.c_void_p(t_recv.data_ptr()))
 
     def solve(self, fetch=True):
         """fetch=False keeps every per-site array on the device (only the 8-byte optimum crosses to the host)."""
@@ -129,11 +152,12 @@ class ShardedTrimming(ShardedResampling):
                 self._exchange_boundary(handle)
             handle.call('dabry_step_trim_refine')
             if self.world > 1:
-                local = handle.cost_map(100, 100, full=False)
-                t = self._tensor(local)
+                import ctypes as C
+                t = self._buffer('cost_map', (100, 100))
+                handle.call('dabry_get_cost_map_device', 0, C.c_void_p(t.data_ptr()))
                 self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN, group=self.group)
-                merged = np.ascontiguousarray(t.cpu().numpy())
-                handle.call('dabry_set_cost_map', nat.dptr(merged))
+                self._sync_collective()
+                handle.call('dabry_set_cost_map_device', C.c_void_p(t.data_ptr()))
             handle.call('dabry_step_trim_close')
         s._invalidate()
         s.i_subframe = s.n_subframes

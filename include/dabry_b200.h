@@ -246,6 +246,14 @@ int dabry_boundary_doubles(dabry_solver* h, int64_t* n);
 int dabry_boundary_count(dabry_solver* h, int64_t* n);
 int dabry_export_boundary(dabry_solver* h, double* packed);
 int dabry_import_boundary(dabry_solver* h, const double* packed);
+/* The same with DEVICE buffers of the caller on the handle's device - the tensors NCCL sends from / receives into - so
+ * that the exchange never touches the host: packets are written / read in place, the cost map (solver_ef.py:825-828) is
+ * copied device to device.  The caller synchronises its own stream before the call; the call returns with the
+ * handle's stream drained, so the buffer can go straight to the collective. */
+int dabry_export_boundary_device(dabry_solver* h, double* d_packed);
+int dabry_import_boundary_device(dabry_solver* h, const double* d_packed);
+int dabry_get_cost_map_device(dabry_solver* h, int32_t full, double* d_out);
+int dabry_set_cost_map_device(dabry_solver* h, const double* d_map);
 
 /* ---- evaluation hooks used by the parity tests ---------------------------------------------------------- */
 /* SolverEF.dyn_augsys(t, y) (solver_ef.py:355-359) for n points: t [n], y [n][4] -> dy [n][4]. */

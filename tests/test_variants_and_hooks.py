@@ -258,6 +258,41 @@ def pinned_inputs_same_result():
 test_pinned_inputs_same_result_hostsim, test_pinned_inputs_same_result_gpu = _both(pinned_inputs_same_result)
 
 
+def block_cache_reuse_is_transparent():
+    """Device blocks parked by a closed solver are handed to the next one (DeviceBlockCache): interleaved solvers of
+    different shapes give the same results as their first run, and dabry_release_cached_memory empties the cache."""
+    from dabry_b200 import _native as nat
+    from dabry_b200.problem import NavigationProblem
+    from dabry_b200.solver_ef import SolverEFResampling
+
+    def run(name, sectors, depth):
+        pb = NavigationProblem.from_name(name).rescale()
+        s = SolverEFResampling(pb, NavigationProblem.time_bound(name), n_costate_sectors=sectors, max_depth=depth,
+                               max_sites=1 << 17)  # 2^17 sites: every per-sample array is above the 1 MB cache floor
+        s.solve()
+        out = (list(s.sites), s.solution_cost, np.stack([site.traj.states[-1] for site in s.sites.values()]))
+        s.close()
+        return out
+
+    shapes = [('linear', 30, 4), ('moving_vortex', 60, 3), ('linear', 30, 4), ('three_vortices', 45, 3),
+              ('moving_vortex', 60, 3)]
+    first = {}
+    for shape in shapes:
+        res = run(*shape)
+        if shape in first:
+            assert res[0] == first[shape][0] and res[1] == first[shape][1]
+            assert np.array_equal(res[2], first[shape][2])
+        else:
+            first[shape] = res
+    assert nat.release_cached_memory(0) == 0
+    again = run(*shapes[0])
+    assert again[0] == first[shapes[0]][0] and np.array_equal(again[2], first[shapes[0]][2])
+
+
+test_block_cache_reuse_is_transparent_hostsim, test_block_cache_reuse_is_transparent_gpu = \
+    _both(block_cache_reuse_is_transparent)
+
+
 def test_root_fan_matches_numpy_and_shards():
     """The threaded, cached root fan equals the reference's expression 1000 (cos, sin)(linspace) bit for bit
     (solver_ef.py:465-467), and a block-cyclic shard is the matching subset of the ring."""
