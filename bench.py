@@ -57,7 +57,9 @@ def build_problem(workload, small=False):
         sc = synthetic.planar_waves(*shape)
         ff = DiscreteFF(sc.values, sc.bounds, Coords.CARTESIAN, force_no_diff=True)
         pb = NavigationProblem(ff, sc.x_init, sc.x_target, sc.srf, bl=sc.bl, tr=sc.tr, name='planar_waves').rescale()
-        return pb, sc.total_duration, dict(max_depth=4, max_dist=0.002), 'planar_waves %dx%dx%d' % shape
+        # max_dist: 2^19 roots refine to ~1.0 M extremals at full size (SURVEY 8d config 3 asks for 0.9 - 1.1 M;
+        # profiles/tune_planar_max_dist.py: 5e-5 -> 918 k, 3e-5 -> 1.077 M)
+        return pb, sc.total_duration, dict(max_depth=4, max_dist=0.002 if small else 4e-5), 'planar_waves %dx%dx%d' % shape
     if workload == 'gyre':
         pb = NavigationProblem.from_name('gyre').rescale()
         return pb, 1.0, dict(max_depth=1), 'gyre analytic'

@@ -19,7 +19,9 @@
 #ifndef DABRY_K_IN_SHARED
 #define DABRY_K_IN_SHARED 0
 #endif
+#ifndef DABRY_FREE_ARC_THREADS
 #define DABRY_FREE_ARC_THREADS 128  // block size of the free-arc kernel (FreeArcPhase::kThreads)
+#endif
 
 namespace dabry {
 
