@@ -17,14 +17,23 @@ import numpy as np
 import torch.distributed as dist
 import parity_util as pu
 from dabry_b200 import _native
-_native.use_library(pu.HOSTSIM_LIB)
+backend = {backend!r}
+if backend == 'nccl':
+    import torch
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    _native.use_library(None)          # the product library, one GPU per rank
+    extra = dict(device=local)
+else:
+    _native.use_library(pu.HOSTSIM_LIB)
+    extra = dict()
 from dabry_b200.problem import NavigationProblem
 from dabry_b200.solver_ef import SolverEFResampling, SolverEFTrimming
 from dabry_b200.distributed import ShardedResampling, ShardedTrimming
-dist.init_process_group('gloo')
+dist.init_process_group(backend)
 pb = NavigationProblem.from_name({case!r}).rescale()
 Runner, Solver = (ShardedTrimming, SolverEFTrimming) if {trimming} else (ShardedResampling, SolverEFResampling)
-runner = Runner(lambda **kw: Solver(pb, max_depth={depth}, n_costate_sectors=30, **kw), 30, block={block})
+runner = Runner(lambda **kw: Solver(pb, max_depth={depth}, n_costate_sectors=30, **kw), 30, block={block}, **extra)
 runner.solve()
 s = runner.solver
 rec = {{'rank': runner.rank, 'names': list(s.sites.keys()), 'cost': runner.global_cost, 'owner': runner.owner_rank,
@@ -37,14 +46,32 @@ dist.destroy_process_group()
 '''
 
 
-@pytest.mark.parametrize('case,depth,trimming,block', [('linear', 5, False, None), ('moving_vortex', 4, False, 5),
-                                                       ('gyre', 6, True, None), ('obstacle', 6, True, 3),
-                                                       ('three_vortices', 5, False, 1)])
+CASES = [('linear', 5, False, None), ('moving_vortex', 4, False, 5), ('gyre', 6, True, None), ('obstacle', 6, True, 3),
+         ('three_vortices', 5, False, 1)]
+
+
+@pytest.mark.parametrize('case,depth,trimming,block', CASES)
 def test_two_rank_sharding_matches_single(case, depth, trimming, block, tmp_path, hostsim):
+    _two_ranks_match_single(case, depth, trimming, block, tmp_path, 'gloo')
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('case,depth,trimming,block', CASES)
+def test_two_gpu_nccl_sharding_matches_single(case, depth, trimming, block, tmp_path, cuda_lib):
+    """The same check on two B200s over NCCL: the ring boundary and the cost map travel device to device
+    (dabry_*_device entry points).  Needs two GPUs (`gpurun --gpus 2`); skipped on a one-GPU box."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    _two_ranks_match_single(case, depth, trimming, block, tmp_path, 'nccl')
+
+
+def _two_ranks_match_single(case, depth, trimming, block, tmp_path, backend):
     import pickle
     import subprocess
     script = tmp_path / 'worker.py'
-    script.write_text(WORKER.format(root=pu.ROOT, case=case, depth=depth, out=str(tmp_path), trimming=trimming, block=block))
+    script.write_text(WORKER.format(root=pu.ROOT, case=case, depth=depth, out=str(tmp_path), trimming=trimming,
+                                    block=block, backend=backend))
     env = dict(os.environ, MASTER_ADDR='127.0.0.1')
     subprocess.run([sys.executable, '-W', 'ignore', '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
                     '--master-addr', '127.0.0.1', '--master-port', '29611', str(script)], check=True, env=env,
