@@ -172,10 +172,13 @@ struct CapturedFlagPhase {  // which work items need the obstacle kernel
     }
 };
 
+#ifndef DABRY_OBSTACLE_MIN_BLOCKS
+#define DABRY_OBSTACLE_MIN_BLOCKS 4  // measured 2 / 3 / 4 / 5 blocks per SM: 2.95 / 2.93 / 2.64 / 2.60 ms (config 4), 8.59 / 8.56 / 8.22 / 8.46 ms (config 3)
+#endif
 template <int FK, int METHOD>
 struct ObstacleArcPhase {  // entry side, feasibility and boundary following for the captured extremals
     static constexpr int kThreads = 128;
-    static constexpr int kMinBlocks = 3;
+    static constexpr int kMinBlocks = DABRY_OBSTACLE_MIN_BLOCKS;
     SiteStore S;
     const int32_t* list;      // the integrate work list (null: base + item)
     const int32_t* captured;  // dense list of captured work items
