@@ -360,6 +360,7 @@ def main():
     launches = int(last['kernel_launches'] - base['kernel_launches'])
     n_sites = int(last['n_sites'])
     cost_resident = handle.solution()[1]
+    cost_global = getattr(runner, 'global_cost', cost_resident) if world > 1 else cost_resident
 
     def reduce_max(x):
         if world == 1:
@@ -472,7 +473,8 @@ def main():
                        'timing': 'cuda events on the library stream' if world == 1 else 'barrier-bracketed wall clock, max over ranks',
                        'wall_ms_per_step': total_wall_ms / args.steps,
                        'phase_ms_rank0': {k: round(v, 3) for k, v in phases.items()},
-                       'arrival_cost_rank0': None if np.isnan(cost_resident) else cost_resident},
+                       'arrival_cost_rank0': None if np.isnan(cost_resident) else cost_resident,
+                       'arrival_cost_global': None if np.isnan(cost_global) else cost_global},
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
         }
         print(json.dumps(line), flush=True)
