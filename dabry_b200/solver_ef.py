@@ -691,6 +691,23 @@ class SolverEFResampling(SolverEF):
         if self.solution_site is not None and self.solution_site.traj_full is not None:
             self.pb.io.save_traj(self.solution_site.traj_full, name='solution')
 
+    def save_rff(self, nt: Optional[int] = None, fmt: Optional[str] = None):
+        """Reachability-front function of the solved front in the legacy `rff` layout the reference's viewer reads
+        (`docs/rff_data_h5_format.txt`, `display/display.py:823-855`): data[k] = V - ts[k] with V the minimum-time map of
+        `cost_map_triangle()` (the device rasteriser, K4) shifted to absolute time, so that {data[k] <= 0} is the set
+        reached by ts[k]; cells no triangle covers stay +inf.  h5 when h5py is available, else npz (same names)."""
+        value = self.cost_map_triangle() + self.t_init
+        ts = self.times if nt is None else np.linspace(self.times[0], self.times[-1], nt)
+        nx, ny = value.shape
+        grid = np.stack(np.meshgrid(np.linspace(self.pb.bl[0], self.pb.tr[0], nx),
+                                    np.linspace(self.pb.bl[1], self.pb.tr[1], ny), indexing='ij'), -1)
+        return self.pb.io.save_rff(value[None, :, :] - ts[:, None, None], ts, grid, self.pb.coords, fmt=fmt)
+
+    def save_trajs_h5(self, filename: str = 'trajectories.h5'):
+        """Every site trajectory in the legacy h5 layout (`docs/traj_data_h5_format.txt`); needs h5py."""
+        sites = self.sites
+        return self.pb.io.save_trajs_h5([s.traj for s in sites.values()], filename, names=list(sites.keys()))
+
     def save_front_bundle(self, name='ef_front'):
         """The whole front in ONE npz (padded trajectories + site records): the usable output at 10^5+ extremals."""
         n = self._n_sites()

@@ -293,6 +293,84 @@ test_block_cache_reuse_is_transparent_hostsim, test_block_cache_reuse_is_transpa
     _both(block_cache_reuse_is_transparent)
 
 
+class _FakeH5Node(dict):
+    """Just enough of h5py.File / Group for the exporters: attrs, create_group, create_dataset."""
+
+    def __init__(self):
+        super().__init__()
+        self.attrs = {}
+
+    def create_group(self, name):
+        self[name] = _FakeH5Node()
+        return self[name]
+
+    def create_dataset(self, name, data=None):
+        self[name] = np.array(data)
+        return self[name]
+
+
+def test_legacy_rff_and_traj_exporters(hostsim, tmp_path, monkeypatch):
+    """The two legacy layouts of the reference's docs (rff: coords + data/ts/grid; trajectories: one group per
+    trajectory with data/ts/controls/adjoints) from a solved front.  h5py is not installed here: the npz fallback is
+    checked on disk, the h5 branch against a stand-in module that records what is written."""
+    import sys
+    import types
+    from dabry_b200.problem import NavigationProblem
+    from dabry_b200.solver_ef import SolverEFResampling
+    pb = NavigationProblem.from_name('linear').rescale()
+    pb.io.set_case_dir(str(tmp_path / 'case'))
+    s = SolverEFResampling(pb, NavigationProblem.time_bound('linear'), max_depth=4)
+    s.solve()
+    path = s.save_rff(fmt='npz')
+    with np.load(path) as f:
+        data, ts, grid = f['data'], f['ts'], f['grid']
+        assert str(f['coords']) == 'cartesian'
+    assert data.shape == (s.times.shape[0], 100, 100) and grid.shape == (100, 100, 2)
+    assert np.array_equal(ts, s.times)
+    value = s.cost_map_triangle()
+    assert np.array_equal(np.isfinite(data[0]), np.isfinite(value))
+    # the front at ts[k] is the zero level set: the reached set grows with k; the cell next to the target centre is
+    # reached after the target disc is entered (the solver's arrival cost) and within the horizon
+    reached = (data <= 0).sum(axis=(1, 2))
+    assert reached[0] <= 1 and np.all(np.diff(reached) >= 0) and reached[-1] > 1000
+    ij = np.unravel_index(np.argmin(np.linalg.norm(grid - pb.x_target, axis=-1)), (100, 100))
+    step = s.times[1] - s.times[0]
+    assert s.solution_cost - step <= value[ij] <= s.times[-1] - s.t_init
+    assert data[-1][ij] <= 0. < data[0][ij]
+    assert np.allclose(grid[0, 0], pb.bl) and np.allclose(grid[-1, -1], pb.tr)
+
+    written = {}
+
+    class File(_FakeH5Node):
+        def __init__(self, path, mode):
+            super().__init__()
+            written[path] = self
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+    fake = types.ModuleType('h5py')
+    fake.File = File
+    monkeypatch.setitem(sys.modules, 'h5py', fake)
+    rff_path = s.save_rff()
+    assert rff_path.endswith('rff.h5')
+    f = written[rff_path]
+    assert f.attrs['coords'] == 'cartesian' and set(f) == {'data', 'ts', 'grid'} and np.array_equal(f['data'], data)
+    traj_path = s.save_trajs_h5()
+    f = written[traj_path]
+    assert len(f) == len(s.sites)
+    name0, site0 = next(iter(s.sites.items()))
+    g = f['0']
+    assert g.attrs['coords'] == 'cartesian' and g.attrs['type'] == 'pmp' and g.attrs['info'] == name0
+    assert g.attrs['last_index'] == len(site0.traj) - 1 and g.attrs['interrupted'] is False
+    assert np.array_equal(g['data'], site0.traj.states) and np.array_equal(g['ts'], site0.traj.times)
+    assert np.array_equal(g['adjoints'], site0.traj.costates, equal_nan=True) and g['controls'].shape == (len(site0.traj),)
+    s.close()
+
+
 def test_root_fan_matches_numpy_and_shards():
     """The threaded, cached root fan equals the reference's expression 1000 (cos, sin)(linspace) bit for bit
     (solver_ef.py:465-467), and a block-cyclic shard is the matching subset of the ring."""
