@@ -91,3 +91,24 @@ def apply_penalty(handle, penalty):
 
 def coords_code(coords):
     return nat.GCS if coords == Coords.GCS else nat.CARTESIAN
+
+
+def flow_evaluator(ff, device=0):
+    """A native handle that holds only the flow field `ff` (analytic program or grid), for `Handle.eval_flow`:
+    w and the Jacobian at arbitrary (t, x) on the device (dabry_eval_flow).  Raises LoweringError for fields outside
+    the supported set and NativeError without a device - there is no host evaluation behind it."""
+    cfg = nat.Config()
+    cfg.abi_version = nat.ABI_VERSION
+    cfg.coords = coords_code(getattr(ff, 'coords', Coords.CARTESIAN))
+    cfg.n_time, cfg.max_depth, cfg.mode_origin = 2, 1, 1
+    cfg.device = device
+    cfg.n_index_per_subframe, cfg.trimming_band_width = 10, 3
+    cfg.cost_map_nx = cfg.cost_map_ny = 2
+    cfg.n_roots = cfg.root_count = 1
+    cfg.max_step, cfg.rtol, cfg.atol, cfg.srf = 1., 1e-3, 1e-6, 1.
+    cfg.target_radius = 1.
+    times = nat.f64(np.array((0., 1.)))
+    cfg.times = nat.dptr(times)
+    handle = nat.Handle(cfg, keepalive=(times,))
+    apply_flow(handle, ff)
+    return handle

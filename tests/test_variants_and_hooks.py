@@ -293,6 +293,37 @@ test_block_cache_reuse_is_transparent_hostsim, test_block_cache_reuse_is_transpa
     _both(block_cache_reuse_is_transparent)
 
 
+def from_ff_device_sampling():
+    """DiscreteFF.from_ff(device=...) (one dabry_eval_flow launch over all nodes) against the reference's node-by-node
+    Python loop (flowfield.py:257-309): same bounds and shapes, values and Jacobians to 1e-12; a field that cannot be
+    lowered raises instead of being sampled on the host."""
+    from dabry_b200.flowfield import DiscreteFF, GyreFF, FlowField, LoweringError
+    from dabry_b200.problem import NavigationProblem
+    pb = NavigationProblem.from_name('moving_vortex')
+    for ff, box, kw in ((pb.model.ff, (pb.bl, pb.tr), dict(nx=14, ny=11, nt=5)),
+                        (GyreFF(0.5, 0.5, 2., 2., 1.), (np.zeros(2), np.ones(2)), dict(nx=12, ny=9))):
+        host = DiscreteFF.from_ff(ff, box, **kw)
+        dev = DiscreteFF.from_ff(ff, box, device=0, **kw)
+        assert host.values.shape == dev.values.shape and np.array_equal(host.bounds, dev.bounds)
+        scale = np.abs(host.values).max()
+        assert np.allclose(host.values, dev.values, rtol=1e-12, atol=1e-12 * scale)
+        assert np.allclose(host.grad_values, dev.grad_values, rtol=1e-12, atol=1e-12 * np.abs(host.grad_values).max())
+        assert dev.coords == host.coords
+
+    class Opaque(FlowField):
+        def value(self, t, x):
+            return np.zeros(2)
+
+        def d_value(self, t, x):
+            return np.zeros((2, 2))
+
+    with pytest.raises(LoweringError):
+        DiscreteFF.from_ff(Opaque(), (np.zeros(2), np.ones(2)), nx=4, ny=4, device=0)
+
+
+test_from_ff_device_sampling_hostsim, test_from_ff_device_sampling_gpu = _both(from_ff_device_sampling)
+
+
 class _FakeH5Node(dict):
     """Just enough of h5py.File / Group for the exporters: attrs, create_group, create_dataset."""
 
