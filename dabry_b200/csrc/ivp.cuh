@@ -56,6 +56,74 @@ struct IvpResult {
     double y_term[N];        // sol(t_term)
 };
 
+// What the rare half of a step hands back: a step in which at least one event changed sign (handle_events + the t_eval
+// samples up to the truncation point, ivp.py:80-131, 694-728).
+template <int N>
+struct EventStep {
+    int32_t eval_i, n_emitted, term_event;  // term_event -1: no terminal event
+    double t_term;
+    double y_term[N];
+};
+
+template <int N, class Events, class Sink>
+DABRY_HD_NOINLINE EventStep<N> event_step(const Dense<N> D, Events& events, Sink& sink, const EvalGrid& grid,
+                                          int* act, int na, double t_old, double t, int eval_i) {
+    EventStep<N> out;
+    out.n_emitted = 0;
+    out.term_event = -1;
+    out.t_term = 0.;
+    double roots[DABRY_MAX_EVENTS];
+    bool any_terminal = false;
+    for (int a = 0; a < na; ++a) {
+        const int e = act[a];
+        roots[a] = brentq([&](double tt) {
+            double yy[N];
+            dense_eval<N>(D, tt, yy);
+            return events.value(e, tt, yy);
+        }, t_old, t);
+        any_terminal = any_terminal || events.terminal(e);
+    }
+    int keep = na;
+    if (any_terminal) {
+        // argsort(roots) on a tiny array (insertion sort, stable), cut after the first terminal
+        for (int a = 1; a < na; ++a) {
+            const double r = roots[a];
+            const int e = act[a];
+            int b = a - 1;
+            while (b >= 0 && roots[b] > r) {
+                roots[b + 1] = roots[b];
+                act[b + 1] = act[b];
+                --b;
+            }
+            roots[b + 1] = r;
+            act[b + 1] = e;
+        }
+        for (int a = 0; a < na; ++a)
+            if (events.terminal(act[a])) {
+                keep = a + 1;
+                break;
+            }
+    }
+    for (int a = 0; a < keep; ++a) events.record(act[a], roots[a]);
+    if (any_terminal) {
+        out.term_event = act[keep - 1];
+        t = roots[keep - 1];
+        out.t_term = t;
+        dense_eval<N>(D, t, out.y_term);
+    }
+    while (eval_i < grid.n) {  // t_eval values <= t (the truncated t) that were not emitted yet
+        const double te = grid.at(eval_i);
+        if (!(te <= t)) break;
+        double yy[N];
+        dense_eval<N>(D, te, yy);
+        sink.emit(eval_i, te, yy);
+        ++eval_i;
+        ++out.n_emitted;
+    }
+    out.eval_i = eval_i;
+    return out;
+}
+
 // Events concept:  int count() const;  bool terminal(int e) const;  double value(int e, double t, const double* y) const;
 //                  void record(int e, double t_root);
 // Sink concept:    void emit(int j, double t, const double* y);     j indexes the un-sliced linspace
@@ -87,6 +155,7 @@ DABRY_HD void solve_ivp(const Rhs& rhs, Events& events, Sink& sink, double t0, d
     int steps_left = step_budget;
     res.status = IVP_FINISHED;
     res.n_emitted = 0;
+    int n_emitted = 0;  // written to res on the way out (res lives in the caller's frame)
     res.term_event = -1;
     res.t_term = 0.;
     bool finished = false;
@@ -103,6 +172,7 @@ DABRY_HD void solve_ivp(const Rhs& rhs, Events& events, Sink& sink, double t0, d
             }
             for (int e = 0; e < ne; ++e) carry->g[e] = g[e];
             res.status = IVP_RUNNING;
+            res.n_emitted = n_emitted;
             return;
         }
         // OdeSolver.step (base.py): a solver already at t_bound finishes without stepping
@@ -114,13 +184,13 @@ DABRY_HD void solve_ivp(const Rhs& rhs, Events& events, Sink& sink, double t0, d
                                                  : rk_step<N>(S, rhs, tf, max_step, rtol, atol, n_attempts);
             if (!ok) {
                 res.status = IVP_FAILED;
+                res.n_emitted = n_emitted;
                 return;
             }
             if (S.t - tf >= 0.) finished = true;
         }
         const double t_old = S.t_old;
-        double t = S.t;
-        bool terminate = false;
+        const double t = S.t;
         int act[DABRY_MAX_EVENTS];
         int na = 0;
         for (int e = 0; e < ne; ++e) {
@@ -128,70 +198,40 @@ DABRY_HD void solve_ivp(const Rhs& rhs, Events& events, Sink& sink, double t0, d
             if (g[e] >= 0. && g_new <= 0.) act[na++] = e;
             g[e] = g_new;
         }
-        // the local interpolant is needed for event roots and for the t_eval samples inside this step; it is built
-        // at ONE place so that the stage values stay in registers (truncation by a terminal event only removes samples)
+        // the local interpolant is needed for event roots and for the t_eval samples inside this step
         const bool sample_due = eval_i < grid.n && grid.at(eval_i) <= t;
         if (na == 0 && !sample_due) continue;
         Dense<N> D;
         if (METHOD == METHOD_RK4) rk4_dense<N>(S, D);
         else rk_dense<N>(S, D);
-        if (na > 0) {
-            // rare path: a copy of the interpolant goes to local memory for the root finder, D itself does not
-            const Dense<N> Dev = D;
-            double roots[DABRY_MAX_EVENTS];
-            bool any_terminal = false;
-            for (int a = 0; a < na; ++a) {
-                const int e = act[a];
-                roots[a] = brentq([&](double tt) {
-                    double yy[N];
-                    dense_eval<N>(Dev, tt, yy);
-                    return events.value(e, tt, yy);
-                }, t_old, t);
-                any_terminal = any_terminal || events.terminal(e);
+        if (na == 0) {
+            // common path, no call in it: the interpolant stays in registers (with the root finder in the same scope it
+            // was written to local memory and read back on every step: 34 LDL/STL per accepted step)
+            while (eval_i < grid.n) {  // t_eval values <= t that were not emitted yet
+                const double te = grid.at(eval_i);
+                if (!(te <= t)) break;
+                double yy[N];
+                dense_eval<N>(D, te, yy);
+                sink.emit(eval_i, te, yy);
+                ++eval_i;
+                ++n_emitted;
             }
-            int keep = na;
-            if (any_terminal) {
-                // argsort(roots) on a tiny array (insertion sort, stable), cut after the first terminal
-                for (int a = 1; a < na; ++a) {
-                    const double r = roots[a];
-                    const int e = act[a];
-                    int b = a - 1;
-                    while (b >= 0 && roots[b] > r) {
-                        roots[b + 1] = roots[b];
-                        act[b + 1] = act[b];
-                        --b;
-                    }
-                    roots[b + 1] = r;
-                    act[b + 1] = e;
-                }
-                for (int a = 0; a < na; ++a)
-                    if (events.terminal(act[a])) {
-                        keep = a + 1;
-                        break;
-                    }
-                terminate = true;
-            }
-            for (int a = 0; a < keep; ++a) events.record(act[a], roots[a]);
-            if (terminate) {
+        } else {
+            // rare path, out of line: roots of the active events, truncation by the first terminal one, samples up to it
+            const EventStep<N> r = event_step<N>(D, events, sink, grid, act, na, t_old, t, eval_i);
+            eval_i = r.eval_i;
+            n_emitted += r.n_emitted;
+            if (r.term_event >= 0) {
                 res.status = IVP_TERMINATED;
-                res.term_event = act[keep - 1];
-                t = roots[keep - 1];
-                res.t_term = t;
-                dense_eval<N>(Dev, t, res.y_term);
+                res.term_event = r.term_event;
+                res.t_term = r.t_term;
+#pragma unroll
+                for (int i = 0; i < N; ++i) res.y_term[i] = r.y_term[i];
                 finished = true;
             }
         }
-        // t_eval values <= t that were not emitted yet
-        while (eval_i < grid.n) {
-            const double te = grid.at(eval_i);
-            if (!(te <= t)) break;
-            double yy[N];
-            dense_eval<N>(D, te, yy);
-            sink.emit(eval_i, te, yy);
-            ++eval_i;
-            ++res.n_emitted;
-        }
     }
+    res.n_emitted = n_emitted;
 }
 
 }  // namespace dabry
