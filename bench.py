@@ -399,7 +399,9 @@ def main():
             s = make_solver(device_roots=False)
             s.solve()
             cost = s.solution_cost
-            d2h = 12 * int(s._arrival_index.shape[0])
+            # what is read back: the optimum (16 B), the slots of the solution sites (compacted on the device) and the
+            # optimal trajectory; the per-site arrival arrays stay on the device until someone asks for them
+            d2h = 16 + 4 * int(s._solution_slots.shape[0])
             if s.solution_site is not None:
                 traj = s.solution_site.traj
                 d2h += int(traj.states.nbytes + traj.times.nbytes + traj.costates.nbytes)

@@ -113,6 +113,7 @@ SIGNATURES = {
                                   c_double_p]),
     'dabry_get_next_nb': (C.c_int, [_H, C.c_int64, C.c_int64, c_int32_p]),
     'dabry_get_arrivals': (C.c_int, [_H, C.c_int64, C.c_int64, c_int32_p, c_double_p]),
+    'dabry_get_solution_sites': (C.c_int, [_H, C.c_double, c_int32_p, C.c_int64, C.POINTER(C.c_int64)]),
     'dabry_get_solution': (C.c_int, [_H, C.POINTER(C.c_int64), c_double_p]),
     'dabry_get_cost_map': (C.c_int, [_H, C.c_int32, c_double_p]),
     'dabry_get_stats': (C.c_int, [_H, C.POINTER(Stats)]),
@@ -292,6 +293,17 @@ class Handle:
         if count:
             self.call('dabry_get_arrivals', first, count, iptr(idx), dptr(cost))
         return idx, cost
+
+    def solution_sites(self, bound):
+        """Ascending slots of the sites with an arrival cost <= bound (device-side compaction)."""
+        n = C.c_int64()
+        cap = 1 << 16
+        out = np.empty(cap, dtype=np.int32)
+        self.call('dabry_get_solution_sites', float(bound), iptr(out), cap, C.byref(n))
+        if n.value > cap:
+            out = np.empty(n.value, dtype=np.int32)
+            self.call('dabry_get_solution_sites', float(bound), iptr(out), n.value, C.byref(n))
+        return out[:n.value].astype(np.int64)
 
     def solution(self):
         site = C.c_int64()

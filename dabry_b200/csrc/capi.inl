@@ -198,6 +198,12 @@ int dabry_get_solution(dabry_solver* h, int64_t* site, double* cost) {
     return DABRY_OK;
 }
 
+int dabry_get_solution_sites(dabry_solver* h, double bound, int32_t* slots, int64_t cap, int64_t* count) {
+    DABRY_GUARD(h);
+    if (!count || cap < 0) return DABRY_ERR_INVALID;
+    return E.get_solution_sites(bound, slots, cap, count);
+}
+
 int dabry_get_cost_map(dabry_solver* h, int32_t full, double* out) {
     DABRY_GUARD(h);
     if (!out) return DABRY_ERR_INVALID;

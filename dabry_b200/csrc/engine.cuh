@@ -250,6 +250,15 @@ struct ArrivalPhase {
     }
 };
 
+struct SolutionFlagPhase {  // solution_sites (solver_ef.py:676-685): arrived, and not costlier than `bound`
+    static constexpr int kThreads = 256;
+    const int32_t* arr_index;
+    const double* arr_cost;
+    double bound;
+    int32_t* flag;
+    DABRY_HD void operator()(int64_t i) const { flag[i] = (arr_index[i] >= 0 && !(arr_cost[i] > bound)) ? 0 : -1; }
+};
+
 struct ValidFlagPhase {  // membership in sites_valid[subframe] (solver_ef.py:803)
     static constexpr int kThreads = 256;
     SiteStore S;
@@ -928,6 +937,19 @@ public:
         if (first < 0 || count < 0 || first + count > n_sites) return fail(DABRY_ERR_INVALID, "site range");
         if (index) be.download(index, d_arr_index + first, sizeof(int32_t) * count);
         if (cost) be.download(cost, d_arr_cost + first, sizeof(double) * count);
+        return check();
+    }
+
+    // slots of the sites whose arrival cost is not above `bound`, ascending (order-preserving compaction on the device):
+    // what check_solutions keeps, without reading the per-site arrival arrays back (12 B per site)
+    int get_solution_sites(double bound, int32_t* slots, int64_t cap, int64_t* count) {
+        if (!arrivals_ready) return fail(DABRY_ERR_INVALID, "call dabry_finish first");
+        *count = 0;
+        if (n_sites == 0) return DABRY_OK;
+        be.launch(n_sites, SolutionFlagPhase{d_arr_index, d_arr_cost, bound, d_request});
+        const int64_t n = be.scan_requests(d_request, n_sites, d_offset, d_list);
+        *count = n;
+        if (slots && n > 0 && n <= cap) be.download(slots, d_list, sizeof(int32_t) * n);
         return check();
     }
 

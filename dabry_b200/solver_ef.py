@@ -598,17 +598,31 @@ class SolverEFResampling(SolverEF):
         handle = self._ensure_handle()
         if not _finished:
             handle.call('dabry_finish')
-        n = self._n_sites()
-        index, cost = handle.arrivals(0, n)
-        self._arrival_index, self._arrival_cost = index, cost
+        self._arrivals = None  # per-site arrays: read back on first access (12 B per site)
         slot, best = handle.solution()
         self._solution_sites = None
         self._solution_slots = np.zeros(0, dtype=np.int64)
         self.solution_site = None
         if slot >= 0:
             self.success = True
-            self._solution_slots = np.nonzero((index >= 0) & ~(cost > 1.15 * best))[0]
+            # sites with `not cost > 1.15 * best` (solver_ef.py:681-684), compacted on the device: a few kB instead of
+            # the arrival arrays of the whole front
+            self._solution_slots = handle.solution_sites(1.15 * best)
             self.solution_site = self._site_by_slot(slot)
+
+    def _fetch_arrivals(self):
+        if getattr(self, '_arrivals', None) is None:
+            self._arrivals = self._ensure_handle().arrivals(0, self._n_sites())
+        return self._arrivals
+
+    @property
+    def _arrival_index(self):
+        """Per site: grid index of the cheapest in-target sample, -1 if the site never enters the target disc."""
+        return self._fetch_arrivals()[0]
+
+    @property
+    def _arrival_cost(self):
+        return self._fetch_arrivals()[1]
 
     @property
     def solution_cost(self):
@@ -718,6 +732,7 @@ class SolverEFResampling(SolverEF):
 
     # ---- device -> host --------------------------------------------------------------------------------------
     def _invalidate(self):
+        self._arrivals = None
         self._n_sites_cache = None
         self._sites = None
         self._records = None

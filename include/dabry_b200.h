@@ -227,6 +227,10 @@ int dabry_get_trajs(dabry_solver* h, int64_t first, int64_t count, double* times
 int dabry_get_next_nb(dabry_solver* h, int64_t first, int64_t count, int32_t* next_nb);
 /* Per-site arrival: grid index of the cheapest in-target sample (-1: never inside) and its cost. */
 int dabry_get_arrivals(dabry_solver* h, int64_t first, int64_t count, int32_t* index, double* cost);
+/* solution_sites (solver_ef.py:676-685): ascending slots of the sites that arrived with a cost not above `bound`
+ * (the caller passes 1.15 x the optimum), compacted on the device.  *count is always set; slots (capacity cap, may be
+ * NULL to query the count) is filled when count <= cap. */
+int dabry_get_solution_sites(dabry_solver* h, double bound, int32_t* slots, int64_t cap, int64_t* count);
 /* solution_site (slot, -1 if none) and its cost; ties -> lowest slot. */
 int dabry_get_solution(dabry_solver* h, int64_t* site, double* cost);
 /* The last trimming cost map [cost_map_nx][cost_map_ny] (solver_ef.py:828), or cost_map_triangle over all sites

@@ -293,6 +293,31 @@ test_block_cache_reuse_is_transparent_hostsim, test_block_cache_reuse_is_transpa
     _both(block_cache_reuse_is_transparent)
 
 
+def solution_sites_compacted_on_device():
+    """check_solutions keeps the sites with `not cost > 1.15 * best` (solver_ef.py:681-684): the device-side compaction
+    (dabry_get_solution_sites) equals that expression on the per-site arrival arrays, which are only read back here."""
+    from dabry_b200.problem import NavigationProblem
+    from dabry_b200.solver_ef import SolverEFResampling
+    for name, depth in (('linear', 6), ('three_vortices', 5), ('moving_vortex', 5)):
+        pb = NavigationProblem.from_name(name).rescale()
+        s = SolverEFResampling(pb, NavigationProblem.time_bound(name), max_depth=depth)
+        s.solve()
+        assert s.success and s._arrivals is None  # nothing per-site has crossed to the host yet
+        best = s.solution_cost
+        idx, cost = s._arrival_index, s._arrival_cost
+        expect = np.nonzero((idx >= 0) & ~(cost > 1.15 * best))[0]
+        assert len(expect) >= 1 and np.array_equal(s._solution_slots, expect)
+        assert {site.name for site in s.solution_sites} == {s._site_by_slot(int(k)).name for k in expect}
+        assert cost[idx >= 0].min() == best
+        none = s._ensure_handle().solution_sites(best * 0.5)
+        assert none.shape == (0,)
+        s.close()
+
+
+test_solution_sites_compacted_on_device_hostsim, test_solution_sites_compacted_on_device_gpu = \
+    _both(solution_sites_compacted_on_device)
+
+
 def from_ff_device_sampling():
     """DiscreteFF.from_ff(device=...) (one dabry_eval_flow launch over all nodes) against the reference's node-by-node
     Python loop (flowfield.py:257-309): same bounds and shapes, values and Jacobians to 1e-12; a field that cannot be
