@@ -140,10 +140,19 @@ struct GhostInitPhase {  // ghost k = the ring root after the last root of local
 #define DABRY_TRACE_FREE_ARC(site, attempts)
 #endif
 
-template <int FK, int METHOD, bool CHUNKED>
+// Small batches (the children a resampling round creates, the reference's own 30-root cases) are bound by the latency
+// of ONE extremal's dependent chain, not by throughput: a few threads integrate up to 100 steps each while the rest of
+// the GPU idles (config 5: 13 such launches of ~1 ms were 40 % of a trimming solve).  LEAN = false is the same source
+// built for that case: one warp per block so that the batch spreads over all SMs, no register cap (255: every node
+// load of a right-hand side in flight at once, no spill on the critical path).
+#ifndef DABRY_WIDE_BATCH  // work items up to which the latency build is launched
+#define DABRY_WIDE_BATCH 16384
+#endif
+
+template <int FK, int METHOD, bool CHUNKED, bool LEAN = true>
 struct FreeArcPhase {  // the hot kernel: one thread per extremal, free arc with events, `budget` RK steps per launch
-    static constexpr int kThreads = DABRY_FREE_ARC_THREADS;
-    static constexpr int kMinBlocks = DABRY_INTEGRATE_MIN_BLOCKS;  // register cap = 65536 / (128 * kMinBlocks)
+    static constexpr int kThreads = LEAN ? DABRY_FREE_ARC_THREADS : 32;
+    static constexpr int kMinBlocks = LEAN ? DABRY_INTEGRATE_MIN_BLOCKS : 1;  // register cap = 65536 / (128 * kMinBlocks)
     SiteStore S;
     const int32_t* list;  // null: sites [base, base + n)
     int32_t base, index_t, budget;
@@ -175,10 +184,10 @@ struct CapturedFlagPhase {  // which work items need the obstacle kernel
 #ifndef DABRY_OBSTACLE_MIN_BLOCKS
 #define DABRY_OBSTACLE_MIN_BLOCKS 4  // measured 2 / 3 / 4 / 5 blocks per SM: 2.95 / 2.93 / 2.64 / 2.60 ms (config 4), 8.59 / 8.56 / 8.22 / 8.46 ms (config 3)
 #endif
-template <int FK, int METHOD>
+template <int FK, int METHOD, bool LEAN = true>
 struct ObstacleArcPhase {  // entry side, feasibility and boundary following for the captured extremals
-    static constexpr int kThreads = 128;
-    static constexpr int kMinBlocks = DABRY_OBSTACLE_MIN_BLOCKS;
+    static constexpr int kThreads = LEAN ? 128 : 32;
+    static constexpr int kMinBlocks = LEAN ? DABRY_OBSTACLE_MIN_BLOCKS : 1;
     SiteStore S;
     const int32_t* list;      // the integrate work list (null: base + item)
     const int32_t* captured;  // dense list of captured work items
@@ -542,6 +551,7 @@ public:
         memset(&S, 0, sizeof(S));
         memset(&stats, 0, sizeof(stats));
         if (const char* env = getenv("DABRY_FREE_CHUNK")) free_chunk = atoi(env);
+        if (const char* env = getenv("DABRY_B200_WIDE_BATCH")) wide_batch = atoll(env);
         times_h.assign(c.times, c.times + c.n_time);
         cfg.times = nullptr;
         P.coords = c.coords;
@@ -1075,6 +1085,9 @@ private:
     int has_ghost = 0;
     int64_t shard_b = 1, n_blocks = 1;
     int round = 0, i_subframe = 0, trim_stage = 0;
+    // work items up to which the latency build of the arc kernels is launched.  The two builds differ in how ptxas
+    // contracts multiply-adds (<= 1 ulp per operation); DABRY_B200_WIDE_BATCH=0 pins every batch to the lean build
+    int64_t wide_batch = DABRY_WIDE_BATCH;
     int free_chunk = DABRY_FREE_CHUNK;  // RK steps per launch of the free-arc kernel (0: whole arc in one launch)
     int64_t last_new = 0;
     int64_t solution_site = -1;
@@ -1253,6 +1266,9 @@ private:
                 if (free_chunk > 0)
                     be.launch(n_cur, FreeArcPhase<kField, kMethod, true>{S, cur, cur_base, index_t, free_chunk,
                                                                          d_counters, d_captured});
+                else if (n_cur <= wide_batch)
+                    be.launch(n_cur, FreeArcPhase<kField, kMethod, false, false>{S, cur, cur_base, index_t, 0,
+                                                                                 d_counters, d_captured});
                 else
                     be.launch(n_cur, FreeArcPhase<kField, kMethod, false>{S, cur, cur_base, index_t, 0, d_counters,
                                                                           d_captured});
@@ -1271,8 +1287,13 @@ private:
             const int64_t n_cap = be.scan_requests(d_captured, n, d_cap_offset, d_cap_list);
             if (n_cap > 0) {
                 dispatch_field(rk4, [&](auto fk, auto method) {
-                    be.launch(n_cap, ObstacleArcPhase<decltype(fk)::value, decltype(method)::value>{
-                                         S, list, d_cap_list, base, index_t, d_counters});
+                    constexpr int kField = decltype(fk)::value, kMethod = decltype(method)::value;
+                    if (n_cap <= wide_batch)
+                        be.launch(n_cap, ObstacleArcPhase<kField, kMethod, false>{S, list, d_cap_list, base, index_t,
+                                                                                  d_counters});
+                    else
+                        be.launch(n_cap, ObstacleArcPhase<kField, kMethod>{S, list, d_cap_list, base, index_t,
+                                                                           d_counters});
                 });
             }
             stats.ms_obstacle += be.toc();
