@@ -370,6 +370,7 @@ public:
         chk(cudaStreamSynchronize(stream_), "D2H sync");
     }
     void zero(void* d, size_t bytes) { chk(cudaMemsetAsync(d, 0, bytes, stream_), "memset"); }
+    void fill_ones(void* d, size_t bytes) { chk(cudaMemsetAsync(d, 0xFF, bytes, stream_), "memset"); }
     void copy2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows) {
         chk(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, cudaMemcpyDeviceToDevice, stream_), "D2D copy");
     }

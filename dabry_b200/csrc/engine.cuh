@@ -709,8 +709,9 @@ public:
         if (S.capacity >= cap && S.n_time == cfg.n_time) {
             // same handle solved again: keep the store, restore the NaN controls / empty neighbour links
             const int64_t cells = (int64_t) cfg.n_time * S.capacity;
-            be.launch(2 * cells, FillF64Phase{(double*) S.ctrl, quiet_nan()});
-            be.launch(cells, FillI32Phase{S.next_nb, -1});
+            // all-ones bytes: a NaN in every control slot, -1 (None) in every neighbour link - one memset each
+            be.fill_ones(S.ctrl, sizeof(Control) * cells);
+            be.fill_ones(S.next_nb, sizeof(int32_t) * cells);
         } else {
             free_store(S);
             memset(&S, 0, sizeof(S));
@@ -1215,8 +1216,8 @@ private:
         Control* nctrl = (Control*) be.alloc(sizeof(Control) * T * cap);
         int32_t* nnb = (int32_t*) be.alloc(sizeof(int32_t) * T * cap);
         if (!nctrl || !nnb) return fail(DABRY_ERR_CAPACITY, "out of device memory (site store)");
-        be.launch(2 * T * cap, FillF64Phase{(double*) nctrl, quiet_nan()});
-        be.launch(T * cap, FillI32Phase{nnb, -1});
+        be.fill_ones(nctrl, sizeof(Control) * T * cap);  // NaN controls, -1 links (all-ones bytes)
+        be.fill_ones(nnb, sizeof(int32_t) * T * cap);
         if (S.ctrl && n_sites > 0) {
             be.copy2d(nctrl, sizeof(Control) * cap, S.ctrl, sizeof(Control) * oc, sizeof(Control) * n_sites, T);
             be.copy2d(nnb, sizeof(int32_t) * cap, S.next_nb, sizeof(int32_t) * oc, sizeof(int32_t) * n_sites, T);

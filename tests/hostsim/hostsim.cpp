@@ -43,6 +43,7 @@ public:
     void upload(void* d, const void* h, size_t n) { memcpy(d, h, n); }
     void download(void* h, const void* d, size_t n) { memcpy(h, d, n); }
     void zero(void* d, size_t n) { memset(d, 0, n); }
+    void fill_ones(void* d, size_t n) { memset(d, 0xFF, n); }
     void copy2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows) {
         for (size_t r = 0; r < rows; ++r) memcpy((char*) dst + r * dpitch, (const char*) src + r * spitch, width);
     }
