@@ -11,9 +11,11 @@ struct dabry_solver {
 
 static thread_local std::string g_create_error;
 
+// every entry point first makes the handle's device current: a process may hold handles on several GPUs
 #define DABRY_GUARD(h)                 \
     if (!(h) || !(h)->eng) return DABRY_ERR_INVALID; \
-    dabry::Engine<DABRY_BACKEND>& E = *(h)->eng
+    dabry::Engine<DABRY_BACKEND>& E = *(h)->eng;     \
+    E.be.activate()
 
 extern "C" {
 
@@ -78,6 +80,7 @@ int dabry_create(const dabry_config* c, dabry_solver** out) {
 
 void dabry_destroy(dabry_solver* h) {
     if (!h) return;
+    if (h->eng) h->eng->be.activate();
     delete h->eng;
     delete h;
 }

@@ -298,6 +298,10 @@ public:
         return true;
     }
 
+    void activate() const {  // make this handle's device current (no-op when it already is)
+        int current = -1;
+        if (stream_ && (cudaGetDevice(&current) != cudaSuccess || current != device_)) cudaSetDevice(device_);
+    }
     bool ok() const { return err_.empty(); }
     const std::string& error() const { return err_; }
     uint64_t launches() const { return launches_; }

@@ -34,6 +34,7 @@ public:
     static bool host_unregister(void*) { return true; }
     static bool release_cached(int) { return true; }
     bool open(int) { return true; }
+    void activate() const {}
     bool ok() const { return true; }
     const std::string& error() const { return err_; }
     uint64_t launches() const { return launches_; }

@@ -99,3 +99,31 @@ def _two_ranks_match_single(case, depth, trimming, block, tmp_path, backend):
     owner = recs[0]['owner']
     assert recs[owner]['local_cost'] == recs[0]['cost']
     assert recs[0]['steps'] == recs[1]['steps'] == single.native_stats()['rk_steps']
+
+
+@pytest.mark.gpu
+def test_two_devices_in_one_process(cuda_lib):
+    """One process, one solver per GPU, calls interleaved: every entry point makes its handle's device current, and the
+    device block cache keeps the blocks of the two devices apart.  Needs two GPUs; skipped on a one-GPU box."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    from dabry_b200.problem import NavigationProblem
+    from dabry_b200.solver_ef import SolverEFResampling
+    pb = NavigationProblem.from_name('moving_vortex').rescale()
+    bound = NavigationProblem.time_bound('moving_vortex')
+    for _ in range(2):  # second pass re-uses parked blocks
+        a = SolverEFResampling(pb, bound, max_depth=4, device=0, max_sites=1 << 17)
+        b = SolverEFResampling(pb, bound, max_depth=4, device=1, max_sites=1 << 17)
+        a.setup()
+        b.setup()
+        for _ in range(4):
+            a.step()
+            b.step()
+        a.check_solutions()
+        b.check_solutions()
+        assert list(a.sites) == list(b.sites) and a.solution_cost == b.solution_cost
+        for name, site in a.sites.items():
+            assert np.array_equal(site.traj.states, b.sites[name].traj.states, equal_nan=True), name
+        b.close()
+        a.close()
