@@ -575,6 +575,7 @@ public:
         for (int a = 0; a < 2; ++a) {
             C.bl[a] = c.bl[a];
             C.tr[a] = c.tr[a];
+            C.cm_inv[a] = (double) ((a == 0 ? c.cost_map_nx : c.cost_map_ny) - 1) / (c.tr[a] - c.bl[a]);
         }
     }
 

@@ -90,6 +90,7 @@ struct SolverParams {
     double max_dist_sq;
     double ff_max_norm;    // max |w| over the grid nodes, <= 0 disables trim_distance (solver_ef.py:459-460)
     double bl[2], tr[2];   // problem box
+    double cm_inv[2];      // (cm_n - 1) / (tr - bl): reciprocal cell size of the cost map, for the bounding-box index ranges
 };
 
 DABRY_HD int site_index_t(const SiteStore& S, int s) { return S.index_t_init[s] + S.n_samples[s] - 1; }
@@ -501,22 +502,22 @@ DABRY_HD void raster_triangle(const SolverParams& C, double* map, double p10, do
     const double den = cross2(v10, v11, v20, v21);
     if (!(fabs(den) > 1e-8)) return;  // np.isclose(cross, 0.): |c| <= atol = 1e-8  (NaN vertices: nothing inside)
     if (den != den) return;
-    const double c02 = cross2(p10, p11, v20, v21);
-    const double c01 = cross2(p10, p11, v10, v11);
     // bounding box in map indices, one cell of margin on each side
-    const double sx = (C.tr[0] - C.bl[0]) / (double) (C.cm_nx - 1), sy = (C.tr[1] - C.bl[1]) / (double) (C.cm_ny - 1);
     const double xmin = dmin(p10, dmin(p20, p30)), xmax = dmax(p10, dmax(p20, p30));
     const double ymin = dmin(p11, dmin(p21, p31)), ymax = dmax(p11, dmax(p21, p31));
     if (!(xmin == xmin) || !(xmax == xmax) || !(ymin == ymin) || !(ymax == ymax)) return;
     // grid nodes that can lie inside: linspace index range of the bounding box, widened by 1e-6 of a cell against
-    // the rounding of the index mapping (the inside test below is the reference's, evaluated per node).  On a dense
-    // front almost every triangle is smaller than a cell and the range is empty.
-    const double ax = (xmin - C.bl[0]) / sx, bx = (xmax - C.bl[0]) / sx;
-    const double ay = (ymin - C.bl[1]) / sy, by = (ymax - C.bl[1]) / sy;
+    // the rounding of the index mapping (the inside test below is the reference's, evaluated per node; the reciprocal
+    // cell size is one rounding, 1e-16, inside that margin).  On a dense front almost every triangle is smaller than a
+    // cell and the range is empty.
+    const double ax = (xmin - C.bl[0]) * C.cm_inv[0], bx = (xmax - C.bl[0]) * C.cm_inv[0];
+    const double ay = (ymin - C.bl[1]) * C.cm_inv[1], by = (ymax - C.bl[1]) * C.cm_inv[1];
     if (!(bx >= -1. && ax <= (double) C.cm_nx && by >= -1. && ay <= (double) C.cm_ny)) return;
     const int i_lo = imax((int) ceil(ax - 1e-6), 0), i_hi = imin((int) floor(bx + 1e-6), C.cm_nx - 1);
     const int j_lo = imax((int) ceil(ay - 1e-6), 0), j_hi = imin((int) floor(by + 1e-6), C.cm_ny - 1);
     if (i_lo > i_hi || j_lo > j_hi) return;
+    const double c02 = cross2(p10, p11, v20, v21);
+    const double c01 = cross2(p10, p11, v10, v11);
     for (int i = i_lo; i <= i_hi; ++i) {
         const double gx = map_coord(C.bl[0], C.tr[0], C.cm_nx, i);
         for (int j = j_lo; j <= j_hi; ++j) {
