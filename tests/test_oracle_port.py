@@ -12,7 +12,7 @@ import pytest
 
 import parity_util as pu
 
-FAST = ['linear_R', 'obstacle_R', 'chertovskih_T', 'big_rankine_T', 'linear_T']
+FAST = ['linear_R', 'obstacle_R', 'chertovskih_T', 'big_rankine_T', 'linear_T', 'era5_like_R', 'spherical_geodesic_R']
 ALL = pu.golden_keys('R') + pu.golden_keys('T')
 CASES_TO_RUN = ALL if os.environ.get('DABRY_ORACLE_ALL') else FAST
 
