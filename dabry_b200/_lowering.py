@@ -40,6 +40,8 @@ def apply_flow(handle, ff):
         hi = nat.f64(np.concatenate(((0.,), b[:, 1])) if not unsteady else b[:, 1])
         handle.call('dabry_set_flow_grid', nat.dptr(values), nat.dptr(grad), nt, nx, ny, 1 if unsteady else 0,
                     nat.dptr(lo), nat.dptr(hi), C.byref(wrapper))
+        # a page-locked array is uploaded in the background (streamed upload): it must outlive the first solve
+        handle._keep = tuple(handle._keep) + (values,)
         return
     if not isinstance(inner, FlowField):
         raise LoweringError(f'{type(inner).__name__} is not a FlowField')

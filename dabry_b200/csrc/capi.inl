@@ -222,6 +222,7 @@ int dabry_get_stats(dabry_solver* h, dabry_stats* out) {
 int dabry_get_flow_max_norm(dabry_solver* h, double* out) {
     DABRY_GUARD(h);
     if (!out) return DABRY_ERR_INVALID;
+    E.finish_grid();  // a streamed upload reduces max |w| while it packs
     *out = E.flow_max_norm;
     return DABRY_OK;
 }

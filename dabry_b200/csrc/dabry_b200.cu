@@ -215,6 +215,12 @@ public:
             cudaStreamSynchronize(stream_);
             for (cudaEvent_t e : {ev0_, ev1_, tot0_, tot1_})
                 if (e) cudaEventDestroy(e);
+            if (copy_stream_) {
+                cudaStreamSynchronize(copy_stream_);
+                for (cudaEvent_t e : copy_ev_)
+                    if (e) cudaEventDestroy(e);
+                cudaStreamDestroy(copy_stream_);
+            }
             if (d_small_) cudaFreeAsync(d_small_, stream_);
             if (d_block_sum_) cudaFreeAsync(d_block_sum_, stream_);
             cudaStreamSynchronize(stream_);
@@ -369,6 +375,33 @@ public:
         chk(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, stream_), "H2D copy");
         chk(cudaStreamSynchronize(stream_), "H2D sync");
     }
+    // background H2D copy of one chunk on the copy stream; wait_chunk orders the compute stream behind it
+    static constexpr int kCopySlots = 8;
+    void upload_chunk_async(void* d, const void* h, size_t bytes, int slot) {
+        if (!copy_stream_) {
+            if (!chk(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking), "cudaStreamCreate")) return;
+            for (int i = 0; i < kCopySlots; ++i) cudaEventCreateWithFlags(&copy_ev_[i], cudaEventDisableTiming);
+        }
+        // the staging buffer was allocated on the compute stream: the copy may not start before that allocation
+        cudaEventRecord(copy_ev_[slot], stream_);
+        cudaStreamWaitEvent(copy_stream_, copy_ev_[slot], 0);
+        chk(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, copy_stream_), "H2D copy (streamed)");
+        chk(cudaEventRecord(copy_ev_[slot], copy_stream_), "event record");
+    }
+    void wait_chunk(int slot) {
+        if (copy_stream_) chk(cudaStreamWaitEvent(stream_, copy_ev_[slot], 0), "stream wait");
+    }
+    void sync_copies() {
+        if (copy_stream_) cudaStreamSynchronize(copy_stream_);
+    }
+    static bool host_is_pinned(const void* p) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        return attr.type == cudaMemoryTypeHost;
+    }
     void download(void* h, const void* d, size_t bytes) {
         chk(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, stream_), "D2H copy");
         chk(cudaStreamSynchronize(stream_), "D2H sync");
@@ -466,7 +499,8 @@ private:
         return false;
     }
     int device_ = 0, sm_count_ = 148;
-    cudaStream_t stream_ = nullptr;
+    cudaStream_t stream_ = nullptr, copy_stream_ = nullptr;
+    cudaEvent_t copy_ev_[kCopySlots] = {};
     std::unordered_map<void*, size_t> live_;  // cacheable blocks this handle holds -> their real size
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr, tot0_ = nullptr, tot1_ = nullptr;
     void* d_small_ = nullptr;

@@ -158,10 +158,12 @@ struct FreeArcPhase {  // the hot kernel: one thread per extremal, free arc with
     int32_t base, index_t, budget;
     Counters* counters;
     int32_t* running;     // -1 / 0 per work item: the arc is parked and continues in the next chunk
+    double t_park = INFINITY;  // CHUNKED: park the arc between two steps once its time reaches t_park (streamed grid)
+    int32_t resume_only = 0;   // CHUNKED: only continue parked arcs (a later window over the same work items)
     DABRY_HD void operator()(int64_t i) const {
         const int s = list ? list[i] : base + (int) i;
         unsigned attempts = 0, calls = 0;
-        site_free_arc<FK, METHOD, CHUNKED>(problem(), S, s, index_t, attempts, calls, budget);
+        site_free_arc<FK, METHOD, CHUNKED>(problem(), S, s, index_t, attempts, calls, budget, t_park, resume_only != 0);
         DABRY_TRACE_FREE_ARC(s, attempts);
         counter_add(&counters->rk_steps, attempts);
         counter_add(&counters->ivp_calls, calls);
@@ -358,6 +360,7 @@ struct PackGridPhase {
     double scaler_speed;             // WrapperFF._scaler_speed
     int32_t f32;                     // store the records in fp32 (dtype F32)
     unsigned long long* max_norm;    // bits of max |scaler * w| over the nodes (non-negative doubles order like integers)
+    int64_t first_record;            // work item 0 is this record
     DABRY_HD void node(int k, int ix, int iy, double* c) const {
         const int64_t n = ((int64_t) k * nx + ix) * ny + iy;
         c[0] = values[2 * n];
@@ -379,7 +382,8 @@ struct PackGridPhase {
         c[4] = (values[2 * xp + 1] - values[2 * xm + 1]) / two_dx;
         c[5] = (values[2 * yp + 1] - values[2 * ym + 1]) / two_dy;
     }
-    DABRY_HD void operator()(int64_t i) const {
+    DABRY_HD void operator()(int64_t item) const {
+        const int64_t i = item + first_record;  // a streamed upload packs the record frames group by group
         const int iy = (int) (i % ny);
         const int ix = (int) ((i / ny) % nx);
         const int k = (int) (i / ((int64_t) ny * nx)) - 1;  // record frame f = k + 1, k = -1 .. nt - 1
@@ -552,6 +556,7 @@ public:
         memset(&stats, 0, sizeof(stats));
         if (const char* env = getenv("DABRY_FREE_CHUNK")) free_chunk = atoi(env);
         if (const char* env = getenv("DABRY_B200_WIDE_BATCH")) wide_batch = atoll(env);
+        if (const char* env = getenv("DABRY_B200_STREAM_UPLOAD")) stream_upload = atoi(env) != 0;
         times_h.assign(c.times, c.times + c.n_time);
         cfg.times = nullptr;
         P.coords = c.coords;
@@ -580,6 +585,7 @@ public:
     }
 
     ~Engine() {
+        drop_pending_grid();
         free_store(S);
         be.free(d_times);
         be.free(d_tables);
@@ -614,6 +620,7 @@ public:
                       const double* lo, const double* hi, const dabry_wrapper* w) {
         if (!values || nt < 1 || nx < 3 || ny < 3 || (!unsteady && nt != 1))
             return fail(DABRY_ERR_INVALID, "flow grid: need values, nt >= 1, nx >= 3, ny >= 3 (nt == 1 if steady)");
+        drop_pending_grid();
         be.tic();
         const int64_t nodes = (int64_t) nt * nx * ny;
         const int64_t records = (int64_t) (nt + 1) * nx * ny;
@@ -623,7 +630,12 @@ public:
         be.free(d_grid);
         d_grid = (double*) be.alloc((cfg.dtype == DABRY_F32 ? sizeof(float) : sizeof(double)) * 12 * records);
         if (!d_values || !d_grid || (grad && !d_grad)) return fail(DABRY_ERR_CAPACITY, "flow grid: out of device memory");
-        be.upload(d_values, values, sizeof(double) * 2 * nodes);
+        // A page-locked `values` array of an unsteady field is uploaded in the background, a group of frames at a time
+        // on the copy stream; the record frames are packed group by group when the first solve needs them and the free
+        // arcs of that solve are parked at the time the next group starts (integrate()).  The caller keeps `values`
+        // alive and unchanged until that solve (or any other call that needs the whole grid) returns.
+        const bool streamed = stream_upload && unsteady && !grad && nt >= 2 * kGridGroups && be.host_is_pinned(values);
+        if (!streamed) be.upload(d_values, values, sizeof(double) * 2 * nodes);
         if (grad) be.upload(d_grad, grad, sizeof(double) * 4 * nodes);
         GridDesc& G = P.field.grid;
         G.data = d_grid;
@@ -642,7 +654,27 @@ public:
         be.zero(d_key, sizeof(unsigned long long));
         const int f32 = cfg.dtype == DABRY_F32 ? 1 : 0;
         PackGridPhase ph{d_values, d_grad, d_grid, nt, nx, ny, 2 * G.spacing[1], 2 * G.spacing[2],
-                         w ? w->scaler_speed : 1., f32, d_key};
+                         w ? w->scaler_speed : 1., f32, d_key, 0};
+        P.field.kind = f32 ? FIELD_GRID_F32 : FIELD_GRID;
+        set_wrapper(w);
+        if (streamed) {
+            const int per = (nt + kGridGroups - 1) / kGridGroups;
+            for (int g = 0; g < kGridGroups; ++g) group_frames[g] = imin((g + 1) * per, nt);
+            pending_pack = ph;
+            pending_values = d_values;
+            pending_host = values;
+            pending_key = d_key;
+            groups_packed = 0;
+            groups_issued = 0;
+            frames_packed = 0;
+            grid_pending = true;
+            // Only the first group is put on the copy engine now: host-to-device copies of all streams share one DMA
+            // queue, and the small uploads of the solve (problem constants, root costates) must not wait behind the
+            // whole grid.  Group g + 1 is issued when group g is packed, right before the window that hides it.
+            issue_group();
+            stats.ms_upload += be.toc();  // issue time only: the copies run behind the caller's back
+            return check();
+        }
         be.launch(records, ph);
         unsigned long long key = 0;
         be.download(&key, d_key, sizeof(key));
@@ -652,10 +684,73 @@ public:
         be.sync();
         be.free(d_values);
         be.free(d_grad);
-        P.field.kind = f32 ? FIELD_GRID_F32 : FIELD_GRID;
-        set_wrapper(w);
         stats.ms_upload += be.toc();
         return check();
+    }
+
+    // ---- streamed grid upload ----
+#ifndef DABRY_GRID_GROUPS
+#define DABRY_GRID_GROUPS 4
+#endif
+    static constexpr int kGridGroups = DABRY_GRID_GROUPS;
+    void drop_pending_grid() {  // a handle destroyed or re-loaded while its grid is still arriving
+        if (!grid_pending) return;
+        be.sync_copies();
+        be.free(pending_key);
+        be.free(pending_values);
+        pending_key = nullptr;
+        pending_values = nullptr;
+        grid_pending = false;
+    }
+    // pack the record frames whose two value frames have arrived with group `upto` (record frame f = k + 1 holds value
+    // frames max(k, 0) and min(k + 1, nt - 1)); after the last group: max |w|, staging buffer released
+    void issue_group() {  // background copy of the next group of value frames
+        if (groups_issued >= kGridGroups) return;
+        const GridDesc& G = P.field.grid;
+        const int g = groups_issued++;
+        const int f0 = g == 0 ? 0 : group_frames[g - 1], f1 = group_frames[g];
+        const size_t frame_doubles = (size_t) 2 * G.nx * G.ny;
+        if (f1 > f0)
+            be.upload_chunk_async(pending_values + f0 * frame_doubles, pending_host + f0 * frame_doubles,
+                                  sizeof(double) * frame_doubles * (size_t) (f1 - f0), g);
+    }
+    void pack_groups(int upto) {
+        const GridDesc& G = P.field.grid;
+        for (; groups_packed <= upto && groups_packed < kGridGroups; ++groups_packed) {
+            const int have = group_frames[groups_packed];  // value frames 0 .. have - 1 are on the device after this group
+            while (groups_issued <= groups_packed) issue_group();
+            be.wait_chunk(groups_packed);
+            issue_group();  // the next group travels while this one is packed and used
+            const int hi = have >= G.nt ? G.nt + 1 : have;  // record frames [frames_packed, hi) are complete
+            if (hi > frames_packed) {
+                PackGridPhase ph = pending_pack;
+                ph.first_record = (int64_t) frames_packed * G.nx * G.ny;
+                be.launch((int64_t) (hi - frames_packed) * G.nx * G.ny, ph);
+                frames_packed = hi;
+            }
+        }
+        if (groups_packed >= kGridGroups && grid_pending) {
+            unsigned long long key = 0;
+            be.download(&key, pending_key, sizeof(key));
+            memcpy(&flow_max_norm, &key, sizeof(key));
+            if (cfg.ff_max_norm < 0.) C.ff_max_norm = flow_max_norm;
+            be.free(pending_key);
+            be.free(pending_values);
+            pending_key = nullptr;
+            pending_values = nullptr;
+            grid_pending = false;
+        }
+    }
+    void finish_grid() {
+        if (grid_pending) pack_groups(kGridGroups - 1);
+    }
+    // solver time before which every right-hand side of a step only touches value frames 0 .. have - 1
+    double park_time(int have) const {
+        const GridDesc& G = P.field.grid;
+        if (have >= G.nt) return INFINITY;
+        const double t_grid = G.lo[0] + (double) (have - 1) * G.spacing[0];  // frame index floor(pos) <= have - 2 below it
+        const double t = (t_grid - P.field.time_origin) / P.field.scale_time;
+        return t - 1.001 * cfg.max_step - 1e-9 * (fabs(t) + 1.);
     }
 
     int set_flow_program(const dabry_leaf* leaves, int n, const double* tables, int64_t n_tab, const dabry_wrapper* w) {
@@ -688,7 +783,7 @@ public:
 
     // ---- solve ----
     int setup(int variant_, const double* costates) {
-        bind();
+        bind(false);
         if (P.field.kind < 0) return fail(DABRY_ERR_INVALID, "no flow field set");
         // theta_0 shard of this handle: contiguous [root_offset, root_offset + root_count) (shard_block == 0), or
         // block-cyclic: blocks of shard_block roots, every shard_world-th block of the ring starting at root_offset
@@ -752,7 +847,7 @@ public:
     }
 
     int step_integrate() {
-        bind();
+        bind(false);
         if (variant == DABRY_TRIMMING) return fail(DABRY_ERR_INVALID, "step_integrate: resampling/simple only");
         if (shoot_end > shoot_begin) {
             if (int rc = integrate(nullptr, shoot_begin, shoot_end - shoot_begin, cfg.n_time - 1)) return rc;
@@ -795,7 +890,7 @@ public:
 
     int step_trim_integrate() {
         if (variant != DABRY_TRIMMING) return fail(DABRY_ERR_INVALID, "not a trimming solve");
-        bind();
+        bind(false);
         if (int rc = ensure_aux(n_sites)) return rc;
         be.tic();
         ValidFlagPhase vf{S, i_subframe, d_request};
@@ -1090,6 +1185,14 @@ private:
     // work items up to which the latency build of the arc kernels is launched.  The two builds differ in how ptxas
     // contracts multiply-adds (<= 1 ulp per operation); DABRY_B200_WIDE_BATCH=0 pins every batch to the lean build
     int64_t wide_batch = DABRY_WIDE_BATCH;
+    // streamed grid upload (set_flow_grid / pack_groups / integrate); DABRY_B200_STREAM_UPLOAD=0 disables it
+    bool stream_upload = true, grid_pending = false;
+    int groups_packed = 0, frames_packed = 0, group_frames[kGridGroups] = {};
+    PackGridPhase pending_pack{};
+    double* pending_values = nullptr;
+    const double* pending_host = nullptr;
+    int groups_issued = 0;
+    unsigned long long* pending_key = nullptr;
     int free_chunk = DABRY_FREE_CHUNK;  // RK steps per launch of the free-arc kernel (0: whole arc in one launch)
     int64_t last_new = 0;
     int64_t solution_site = -1;
@@ -1107,7 +1210,11 @@ private:
         F.scaler_dspeed = w ? w->scaler_dspeed : 1.;
     }
 
-    void bind() { be.set_problem(P); }
+    // need_grid = false: the caller copes with a grid that is still arriving (setup; integrate packs it in windows)
+    void bind(bool need_grid = true) {
+        if (need_grid) finish_grid();
+        be.set_problem(P);
+    }
 
     template <int V>
     struct Tag {
@@ -1262,6 +1369,25 @@ private:
         int32_t cur_base = base;
         int64_t n_cur = n;
         int flip = 0;
+        if (grid_pending) {
+            // the grid is still arriving: one window of free arcs per group of frames, every arc parked (IvpCarry) at the
+            // time the frames that are on the device run out, while the copy stream brings the next group
+            bool first = true;
+            while (grid_pending) {
+                const int g = groups_packed;
+                pack_groups(g);
+                const double t_park = park_time(group_frames[g]);
+                dispatch_field(rk4, [&](auto fk, auto method) {
+                    FreeArcPhase<decltype(fk)::value, decltype(method)::value, true> ph{
+                        S, list, base, index_t, 0x7fffffff, d_counters, d_captured};
+                    ph.t_park = t_park;
+                    ph.resume_only = first ? 0 : 1;
+                    be.launch(n, ph);
+                });
+                first = false;
+            }
+            n_cur = 0;  // the last window ran every arc to its end
+        }
         while (n_cur > 0) {
             dispatch_field(rk4, [&](auto fk, auto method) {
                 constexpr int kField = decltype(fk)::value, kMethod = decltype(method)::value;

@@ -130,7 +130,8 @@ DABRY_HD_NOINLINE EventStep<N> event_step(const Dense<N> D, Events& events, Sink
 template <int N, int METHOD, class KS = KRegisters<N>, class Rhs, class Events, class Sink>
 DABRY_HD void solve_ivp(const Rhs& rhs, Events& events, Sink& sink, double t0, double tf, const double* y0,
                         const EvalGrid& grid, double max_step, double rtol, double atol, IvpResult<N>& res,
-                        unsigned& n_attempts, IvpCarry<N>* carry = nullptr, int step_budget = 0, KS kstore = KS()) {
+                        unsigned& n_attempts, IvpCarry<N>* carry = nullptr, int step_budget = 0, KS kstore = KS(),
+                        double t_park = INFINITY) {
     RkState<N, KS> S;
     S.K = kstore;
     const int ne = events.count();
@@ -160,7 +161,8 @@ DABRY_HD void solve_ivp(const Rhs& rhs, Events& events, Sink& sink, double t0, d
     res.t_term = 0.;
     bool finished = false;
     while (!finished) {
-        if (carry && step_budget > 0 && steps_left-- == 0) {  // budget spent between two steps: park the state
+        // budget spent, or the time reached up to which the caller can serve the right-hand side: park between two steps
+        if (carry && ((step_budget > 0 && steps_left-- == 0) || S.t >= t_park)) {
             carry->started = 1;
             carry->eval_i = eval_i;
             carry->t = S.t;

@@ -216,9 +216,10 @@ struct ConstrSink {
 // A terminal obstacle event leaves the entry record (obstacle, t_enter_obs, index_t_obs, state at entry) for part B.
 template <int FK, int METHOD, bool CHUNKED>
 DABRY_HD void site_free_arc(const ProblemDev& P, const SiteStore& S, int s, int index_t, unsigned& n_attempts,
-                            unsigned& n_calls, int step_budget) {
+                            unsigned& n_calls, int step_budget, double t_park = INFINITY, bool resume_only = false) {
     IvpCarry<4> carry;
     int idx0;
+    if (CHUNKED && resume_only && !(S.flags[s] & SITE_RUNNING)) return;  // finished in an earlier window
     if (CHUNKED && (S.flags[s] & SITE_RUNNING)) {  // re-entry after a chunk of steps
         idx0 = S.arc_from[s];
         carry.started = 1;
@@ -252,10 +253,11 @@ DABRY_HD void site_free_arc(const ProblemDev& P, const SiteStore& S, int s, int 
     __shared__ double k_tile[8 * 4 * DABRY_FREE_ARC_THREADS];
     solve_ivp<4, METHOD, KShared<4, DABRY_FREE_ARC_THREADS>>(
         rhs, ev, sink, grid.at(0), grid.at(n - 1), y0, grid, P.max_step, P.rtol, P.atol, res, n_attempts,
-        CHUNKED ? &carry : nullptr, CHUNKED ? step_budget : 0, KShared<4, DABRY_FREE_ARC_THREADS>{k_tile + threadIdx.x});
+        CHUNKED ? &carry : nullptr, CHUNKED ? step_budget : 0, KShared<4, DABRY_FREE_ARC_THREADS>{k_tile + threadIdx.x},
+        t_park);
 #else
     solve_ivp<4, METHOD>(rhs, ev, sink, grid.at(0), grid.at(n - 1), y0, grid, P.max_step, P.rtol, P.atol, res, n_attempts,
-                         CHUNKED ? &carry : nullptr, CHUNKED ? step_budget : 0);
+                         CHUNKED ? &carry : nullptr, CHUNKED ? step_budget : 0, KRegisters<4>(), t_park);
 #endif
     S.n_samples[s] += res.n_emitted;
     if (CHUNKED && res.status == IVP_RUNNING) {

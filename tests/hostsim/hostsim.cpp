@@ -43,6 +43,12 @@ public:
     void free(T* p) { ::free((void*) p); }
     void upload(void* d, const void* h, size_t n) { memcpy(d, h, n); }
     void download(void* h, const void* d, size_t n) { memcpy(h, d, n); }
+    // streamed grid upload: the serial double copies at once; DABRY_HOSTSIM_STREAMED=1 makes every host array count as
+    // page-locked so that the CPU tier runs the windowed free arcs
+    void upload_chunk_async(void* d, const void* h, size_t n, int) { memcpy(d, h, n); }
+    void wait_chunk(int) {}
+    void sync_copies() {}
+    static bool host_is_pinned(const void*) { return getenv("DABRY_HOSTSIM_STREAMED") != nullptr; }
     void zero(void* d, size_t n) { memset(d, 0, n); }
     void fill_ones(void* d, size_t n) { memset(d, 0xFF, n); }
     void copy2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows) {

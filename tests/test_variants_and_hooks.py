@@ -293,6 +293,53 @@ test_block_cache_reuse_is_transparent_hostsim, test_block_cache_reuse_is_transpa
     _both(block_cache_reuse_is_transparent)
 
 
+def streamed_grid_upload_is_bit_identical(monkeypatch, exact=True):
+    """A page-locked unsteady grid is uploaded in the background in four groups of frames; the first solve packs the
+    record frames group by group and parks every free arc (IvpCarry) at the time the frames on the device run out.
+    Results, step counts and max |w| must equal the one-shot upload bit for bit; so must a Trimming solve and the
+    evaluation hooks, which wait for the whole grid."""
+    from dabry_b200.solver_ef import SolverEFResampling, SolverEFTrimming
+    monkeypatch.setenv('DABRY_HOSTSIM_STREAMED', '1')  # tests/hostsim: treat host arrays as page-locked
+    monkeypatch.setenv('DABRY_B200_WIDE_BATCH', '0')   # one build of the arc kernels on both sides of the comparison
+    for cls, kw in ((SolverEFResampling, dict(n_costate_sectors=96, max_depth=3)),
+                    (SolverEFTrimming, dict(n_costate_sectors=48, max_depth=3))):
+        runs = []
+        for streamed in ('0', '1'):
+            monkeypatch.setenv('DABRY_B200_STREAM_UPLOAD', streamed)
+            pb, _ = _synthetic('era5_like', (12, 72, 37))
+            pb.model.ff.ff.pin_memory()
+            s = cls(pb, 0.25, **kw)
+            s.solve()
+            st = s.native_stats()
+            x = np.array([[0.1, -0.9, 0.7]]).T * np.ones((1, 2)) * 0.5
+            flow = s._ensure_handle().eval_flow(np.array([0.01, 0.1, 0.2]), x)
+            runs.append((list(s.sites), {n: (site.traj.states.copy(), site.traj.costates.copy(), site.closure_reason)
+                                        for n, site in s.sites.items()},
+                         st['rk_steps'], st['ivp_calls'], s.solution_cost, s._ff_max_norm, flow, st['kernel_launches']))
+            s.close()
+        a, b = runs
+        assert a[0] == b[0] and a[2:4] == b[2:4] and a[5] == b[5]
+        assert a[4] == b[4] or (np.isnan(a[4]) and np.isnan(b[4]))
+        for n in a[0]:
+            if exact:
+                assert np.array_equal(a[1][n][0], b[1][n][0], equal_nan=True), n
+                assert np.array_equal(a[1][n][1], b[1][n][1], equal_nan=True), n
+            else:  # two builds of the kernel: ptxas contracts multiply-adds differently (<= 1 ulp per operation)
+                assert np.allclose(a[1][n][0], b[1][n][0], rtol=1e-9, atol=1e-9, equal_nan=True), n
+            assert a[1][n][2] == b[1][n][2]
+        assert np.array_equal(a[6][0], b[6][0]) and np.array_equal(a[6][1], b[6][1])
+        assert b[7] > a[7]  # the streamed run really went through the windowed launches
+
+
+def test_streamed_grid_upload_is_bit_identical_hostsim(hostsim, monkeypatch):
+    streamed_grid_upload_is_bit_identical(monkeypatch)
+
+
+@pytest.mark.gpu
+def test_streamed_grid_upload_is_bit_identical_gpu(cuda_lib, monkeypatch):
+    streamed_grid_upload_is_bit_identical(monkeypatch, exact=False)
+
+
 def solution_sites_compacted_on_device():
     """check_solutions keeps the sites with `not cost > 1.15 * best` (solver_ef.py:681-684): the device-side compaction
     (dabry_get_solution_sites) equals that expression on the per-site arrival arrays, which are only read back here."""
