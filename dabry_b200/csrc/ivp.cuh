@@ -13,7 +13,7 @@ namespace dabry {
 
 #define DABRY_MAX_EVENTS (1 + DABRY_MAX_OBSTACLES)
 
-enum IvpStatus : int32_t { IVP_FINISHED = 0, IVP_TERMINATED = 1, IVP_FAILED = -1, IVP_RUNNING = 2 };
+enum IvpStatus : int32_t { IVP_FINISHED = 0, IVP_TERMINATED = 1, IVP_FAILED = -1, IVP_RUNNING = 2, IVP_DEFERRED = 3 };
 
 // Everything solve_ivp carries from one step to the next.  With a step budget the driver loop can be left after any
 // step and re-entered later with bit-identical results, which lets the engine re-pack the still-running extremals into
@@ -148,8 +148,13 @@ DABRY_HD void solve_ivp(const Rhs& rhs, Events& events, Sink& sink, double t0, d
         for (int e = 0; e < ne; ++e) g[e] = carry->g[e];
         eval_i = carry->eval_i;
     } else {
-        if (METHOD == METHOD_RK4) rk4_init<N>(S, rhs, t0, y0, max_step);
-        else rk_init<N>(S, rhs, t0, y0, tf, max_step, rtol, atol);
+        if (METHOD == METHOD_RK4) {
+            rk4_init<N>(S, rhs, t0, y0, max_step);
+        } else if (!rk_init<N>(S, rhs, t0, y0, tf, max_step, rtol, atol, carry ? t_park + max_step : INFINITY)) {
+            res.status = IVP_DEFERRED;  // the initial-step probe needs flow data that has not arrived: start again later
+            res.n_emitted = 0;
+            return;
+        }
         for (int e = 0; e < ne; ++e) g[e] = events.value(e, t0, y0);
         eval_i = grid.first;
     }

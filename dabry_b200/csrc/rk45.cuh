@@ -80,8 +80,8 @@ DABRY_HD void put_stage(KS& K, int stage, const double* k) {
 
 // RungeKutta.__init__ (rk.py:86-103): f0 and the empirical first step.  Costs 2 RHS evaluations.
 template <int N, class KS, class Rhs>
-DABRY_HD void rk_init(RkState<N, KS>& S, const Rhs& rhs, double t0, const double* y0, double t_bound, double max_step,
-                      double rtol, double atol) {
+DABRY_HD bool rk_init(RkState<N, KS>& S, const Rhs& rhs, double t0, const double* y0, double t_bound, double max_step,
+                      double rtol, double atol, double t_data = INFINITY) {
     S.t = t0;
     S.t_old = t0;
 #pragma unroll
@@ -94,7 +94,7 @@ DABRY_HD void rk_init(RkState<N, KS>& S, const Rhs& rhs, double t0, const double
     const double interval = fabs(t_bound - t0);
     if (interval == 0.) {
         S.h_abs = 0.;
-        return;
+        return true;
     }
     double scale[N];
 #pragma unroll
@@ -103,6 +103,9 @@ DABRY_HD void rk_init(RkState<N, KS>& S, const Rhs& rhs, double t0, const double
     const double d1 = rms_norm_scaled<N>(f0, scale);
     double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
     h0 = dmin(h0, interval);
+    // t_data: time up to which the caller can serve the right-hand side (streamed flow grid).  The probe below is the one
+    // evaluation whose distance from t0 the step limit does not bound: if it falls beyond, the start is deferred.
+    if (t0 + h0 > t_data) return false;
     double y1[N], f1[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) y1[i] = S.y[i] + h0 * f0[i];
@@ -114,6 +117,7 @@ DABRY_HD void rk_init(RkState<N, KS>& S, const Rhs& rhs, double t0, const double
     if (d1 <= 1e-15 && d2 <= 1e-15) h1 = dmax(1e-6, h0 * 1e-3);
     else h1 = pow(0.01 / dmax(d1, d2), 1. / 5.);
     S.h_abs = dmin(dmin(100 * h0, h1), dmin(interval, max_step));
+    return true;
 }
 
 // One accepted step of RungeKutta._step_impl (rk.py:111-176).  Returns false on TOO_SMALL_STEP.

@@ -32,7 +32,8 @@ struct Control {
     double u0, u1;
 };
 
-enum SiteFlags : int32_t { SITE_GHOST = 1, SITE_CONNECTED = 2, SITE_PENDING_ENTRY = 4, SITE_RUNNING = 8 };
+enum SiteFlags : int32_t { SITE_GHOST = 1, SITE_CONNECTED = 2, SITE_PENDING_ENTRY = 4, SITE_RUNNING = 8,
+                           SITE_DEFERRED = 16 };  // DEFERRED: the arc could not start in this window (streamed grid)
 
 struct SiteStore {
     int32_t n_time;
@@ -219,7 +220,8 @@ DABRY_HD void site_free_arc(const ProblemDev& P, const SiteStore& S, int s, int 
                             unsigned& n_calls, int step_budget, double t_park = INFINITY, bool resume_only = false) {
     IvpCarry<4> carry;
     int idx0;
-    if (CHUNKED && resume_only && !(S.flags[s] & SITE_RUNNING)) return;  // finished in an earlier window
+    if (CHUNKED && resume_only && !(S.flags[s] & (SITE_RUNNING | SITE_DEFERRED))) return;  // finished in an earlier window
+    if (CHUNKED) S.flags[s] &= ~SITE_DEFERRED;
     if (CHUNKED && (S.flags[s] & SITE_RUNNING)) {  // re-entry after a chunk of steps
         idx0 = S.arc_from[s];
         carry.started = 1;
@@ -259,6 +261,11 @@ DABRY_HD void site_free_arc(const ProblemDev& P, const SiteStore& S, int s, int 
     solve_ivp<4, METHOD>(rhs, ev, sink, grid.at(0), grid.at(n - 1), y0, grid, P.max_step, P.rtol, P.atol, res, n_attempts,
                          CHUNKED ? &carry : nullptr, CHUNKED ? step_budget : 0, KRegisters<4>(), t_park);
 #endif
+    if (CHUNKED && res.status == IVP_DEFERRED) {  // nothing happened yet: a later window starts this arc afresh
+        S.flags[s] |= SITE_DEFERRED;
+        --n_calls;
+        return;
+    }
     S.n_samples[s] += res.n_emitted;
     if (CHUNKED && res.status == IVP_RUNNING) {
         S.flags[s] |= SITE_RUNNING;

@@ -38,7 +38,13 @@ public:
     bool ok() const { return true; }
     const std::string& error() const { return err_; }
     uint64_t launches() const { return launches_; }
-    void* alloc(size_t bytes) { return malloc(bytes ? bytes : 8); }
+    // fresh "device" memory is poisoned (all-ones bytes: NaN doubles, -1 ints) so that a read of something the engine
+    // never wrote - e.g. a record frame of a streamed grid that has not been packed yet - changes results in the CPU tier
+    void* alloc(size_t bytes) {
+        void* p = malloc(bytes ? bytes : 8);
+        if (p) memset(p, 0xFF, bytes ? bytes : 8);
+        return p;
+    }
     template <class T>
     void free(T* p) { ::free((void*) p); }
     void upload(void* d, const void* h, size_t n) { memcpy(d, h, n); }

@@ -302,7 +302,9 @@ def streamed_grid_upload_is_bit_identical(monkeypatch, exact=True):
     monkeypatch.setenv('DABRY_HOSTSIM_STREAMED', '1')  # tests/hostsim: treat host arrays as page-locked
     monkeypatch.setenv('DABRY_B200_WIDE_BATCH', '0')   # one build of the arc kernels on both sides of the comparison
     for cls, kw in ((SolverEFResampling, dict(n_costate_sectors=96, max_depth=3)),
-                    (SolverEFTrimming, dict(n_costate_sectors=48, max_depth=3))):
+                    (SolverEFTrimming, dict(n_costate_sectors=48, max_depth=3)),
+                    (SolverEFResampling, dict(n_costate_sectors=64, max_depth=2, dtype='f32')),
+                    (SolverEFResampling, dict(n_costate_sectors=64, max_depth=2, integrator='rk4'))):
         runs = []
         for streamed in ('0', '1'):
             monkeypatch.setenv('DABRY_B200_STREAM_UPLOAD', streamed)
@@ -329,6 +331,38 @@ def streamed_grid_upload_is_bit_identical(monkeypatch, exact=True):
             assert a[1][n][2] == b[1][n][2]
         assert np.array_equal(a[6][0], b[6][0]) and np.array_equal(a[6][1], b[6][1])
         assert b[7] > a[7]  # the streamed run really went through the windowed launches
+
+
+def test_streamed_upload_defers_starts_whose_probe_outruns_the_frames(hostsim, monkeypatch):
+    """select_initial_step probes the right-hand side at t0 + h0, a distance the step limit does not bound.  With a grid
+    whose frames span 2 % of the horizon the probe of every root falls beyond the frames of the first windows: the start
+    is deferred (IVP_DEFERRED) to the window in which the data is there, and the results still equal the one-shot
+    upload bit for bit."""
+    from dabry_b200 import synthetic
+    from dabry_b200.flowfield import DiscreteFF
+    from dabry_b200.misc import Coords
+    from dabry_b200.problem import NavigationProblem
+    from dabry_b200.solver_ef import SolverEFResampling
+    monkeypatch.setenv('DABRY_HOSTSIM_STREAMED', '1')
+    runs = []
+    for streamed in ('0', '1'):
+        monkeypatch.setenv('DABRY_B200_STREAM_UPLOAD', streamed)
+        sc = synthetic.era5_like(8, 72, 37)
+        bounds = sc.bounds.copy()
+        bounds[0, 1] = bounds[0, 0] + 0.02 * (bounds[0, 1] - bounds[0, 0])  # eight frames inside the first 2 %
+        ff = DiscreteFF(sc.values, bounds, Coords.GCS)
+        ff.pin_memory()
+        pb = NavigationProblem(ff, sc.x_init, sc.x_target, sc.srf, bl=sc.bl, tr=sc.tr).rescale()
+        s = SolverEFResampling(pb, 0.25, n_costate_sectors=48, max_depth=2)
+        s.solve()
+        st = s.native_stats()
+        runs.append((list(s.sites), {n: site.traj.states.copy() for n, site in s.sites.items()}, st['rk_steps'],
+                     st['ivp_calls'], st['kernel_launches']))
+        s.close()
+    a, b = runs
+    assert a[0] == b[0] and a[2:4] == b[2:4] and b[4] > a[4]
+    for n in a[0]:
+        assert np.array_equal(a[1][n], b[1][n], equal_nan=True), n
 
 
 def test_streamed_grid_upload_is_bit_identical_hostsim(hostsim, monkeypatch):
