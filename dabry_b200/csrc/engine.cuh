@@ -556,7 +556,7 @@ public:
         memset(&stats, 0, sizeof(stats));
         if (const char* env = getenv("DABRY_FREE_CHUNK")) free_chunk = atoi(env);
         if (const char* env = getenv("DABRY_B200_WIDE_BATCH")) wide_batch = atoll(env);
-        if (const char* env = getenv("DABRY_B200_STREAM_UPLOAD")) stream_upload = atoi(env) != 0;
+        if (const char* env = getenv("DABRY_B200_STREAM_UPLOAD")) stream_upload = atoi(env);
         times_h.assign(c.times, c.times + c.n_time);
         cfg.times = nullptr;
         P.coords = c.coords;
@@ -634,7 +634,10 @@ public:
         // on the copy stream; the record frames are packed group by group when the first solve needs them and the free
         // arcs of that solve are parked at the time the next group starts (integrate()).  The caller keeps `values`
         // alive and unchanged until that solve (or any other call that needs the whole grid) returns.
-        const bool streamed = stream_upload && unsteady && !grad && nt >= 2 * kGridGroups && be.host_is_pinned(values);
+        // (only grids whose copy takes longer than the extra launches of the windows cost: 64 MB is 1.3 ms of PCIe)
+        const bool big = stream_upload > 1 || sizeof(double) * 2 * (size_t) nodes >= ((size_t) 64 << 20);
+        const bool streamed = stream_upload && big && unsteady && !grad && nt >= 2 * kGridGroups &&
+                              (!w || w->scale_time > 0.) && be.host_is_pinned(values);
         if (!streamed) be.upload(d_values, values, sizeof(double) * 2 * nodes);
         if (grad) be.upload(d_grad, grad, sizeof(double) * 4 * nodes);
         GridDesc& G = P.field.grid;
@@ -1186,7 +1189,8 @@ private:
     // contracts multiply-adds (<= 1 ulp per operation); DABRY_B200_WIDE_BATCH=0 pins every batch to the lean build
     int64_t wide_batch = DABRY_WIDE_BATCH;
     // streamed grid upload (set_flow_grid / pack_groups / integrate); DABRY_B200_STREAM_UPLOAD=0 disables it
-    bool stream_upload = true, grid_pending = false;
+    int stream_upload = 1;  // 0: never, 1: grids of 64 MB and more, 2: every eligible grid (tests)
+    bool grid_pending = false;
     int groups_packed = 0, frames_packed = 0, group_frames[kGridGroups] = {};
     PackGridPhase pending_pack{};
     double* pending_values = nullptr;

@@ -181,7 +181,7 @@ int dabry_release_cached_memory(int32_t device);
  * (nx, ny, 2) when unsteady == 0 (then nt must be 1).  grad: (..., 2, 2) or NULL -> compute_derivatives
  * (flowfield.py:474-504) runs on the device.  lo/hi: bounds[:, 0] / bounds[:, 1] for (t, x, y) (t ignored when
  * steady).  The library repacks into its own HBM layout; the caller's arrays are not retained - with one exception:
- * a PAGE-LOCKED `values` array (dabry_host_register) of an unsteady field without `grad` is uploaded in the
+ * a PAGE-LOCKED `values` array (dabry_host_register) of 64 MB or more of an unsteady field without `grad` is uploaded in the
  * background in groups of time frames, and the first solve packs and uses them as they arrive (its free arcs are
  * parked at the time the frames on the device run out).  Such an array must stay alive and unchanged until the next
  * call that needs the whole grid returns (dabry_solve / dabry_step*, dabry_eval_*, dabry_get_flow_max_norm).

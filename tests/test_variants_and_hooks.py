@@ -306,7 +306,7 @@ def streamed_grid_upload_is_bit_identical(monkeypatch, exact=True):
                     (SolverEFResampling, dict(n_costate_sectors=64, max_depth=2, dtype='f32')),
                     (SolverEFResampling, dict(n_costate_sectors=64, max_depth=2, integrator='rk4'))):
         runs = []
-        for streamed in ('0', '1'):
+        for streamed in ('0', '2'):
             monkeypatch.setenv('DABRY_B200_STREAM_UPLOAD', streamed)
             pb, _ = _synthetic('era5_like', (12, 72, 37))
             pb.model.ff.ff.pin_memory()
@@ -345,7 +345,7 @@ def test_streamed_upload_defers_starts_whose_probe_outruns_the_frames(hostsim, m
     from dabry_b200.solver_ef import SolverEFResampling
     monkeypatch.setenv('DABRY_HOSTSIM_STREAMED', '1')
     runs = []
-    for streamed in ('0', '1'):
+    for streamed in ('0', '2'):
         monkeypatch.setenv('DABRY_B200_STREAM_UPLOAD', streamed)
         sc = synthetic.era5_like(8, 72, 37)
         bounds = sc.bounds.copy()
