@@ -331,6 +331,29 @@ def streamed_grid_upload_is_bit_identical(monkeypatch, exact=True):
             assert a[1][n][2] == b[1][n][2]
         assert np.array_equal(a[6][0], b[6][0]) and np.array_equal(a[6][1], b[6][1])
         assert b[7] > a[7]  # the streamed run really went through the windowed launches
+    # the step-by-step API on a streamed grid (setup / step / check_solutions), then a second solve on the same handle
+    monkeypatch.setenv('DABRY_B200_STREAM_UPLOAD', '2')
+    pb, _ = _synthetic('era5_like', (12, 72, 37))
+    pb.model.ff.ff.pin_memory()
+    one = SolverEFResampling(pb, 0.25, n_costate_sectors=96, max_depth=3)
+    one.solve()
+    two = SolverEFResampling(pb, 0.25, n_costate_sectors=96, max_depth=3)
+    two.setup()
+    for _ in range(3):
+        two.step()
+    two.check_solutions()
+    assert list(one.sites) == list(two.sites)
+    first = {n: site.traj.states.copy() for n, site in one.sites.items()}
+    for n, site in two.sites.items():
+        assert np.array_equal(first[n], site.traj.states, equal_nan=True), n
+    one.solve()  # the grid is resident now: one-launch free arcs
+    for n, site in one.sites.items():
+        if exact:
+            assert np.array_equal(first[n], site.traj.states, equal_nan=True), n
+        else:
+            assert np.allclose(first[n], site.traj.states, rtol=1e-9, atol=1e-9, equal_nan=True), n
+    one.close()
+    two.close()
 
 
 def test_streamed_upload_defers_starts_whose_probe_outruns_the_frames(hostsim, monkeypatch):
