@@ -102,6 +102,7 @@ struct InitRootsPhase {
         const int64_t o = S.at(s, 0);
         S.xp[o] = Sample{x0, x1, p0, p1};
         S.tt[o] = t_init;
+        arrival_note(problem(), S, s, 0, x0, x1);  // a start inside the target disc arrives at cost 0
         S.dyadic[s] = g << max_depth;
         S.valid_first[s] = 0;
         S.valid_last[s] = 0;
@@ -252,10 +253,18 @@ struct ArrivalPhase {
     SiteStore S;
     int32_t* arr_index;
     double* arr_cost;
+    int32_t rescan;  // 1: recompute from the trajectories (site_arrival) instead of trusting the running records
     DABRY_HD void operator()(int64_t i) const {
         double c = 0.;
         int k = -1;
-        if (!(S.flags[i] & SITE_GHOST)) k = site_arrival(problem(), S, (int) i, c);
+        if (!(S.flags[i] & SITE_GHOST)) {
+            if (rescan) {
+                k = site_arrival(problem(), S, (int) i, c);
+            } else {
+                k = S.arr_index[i];  // kept up to date by every writer of a sample (arrival_note)
+                c = S.arr_cost[i];
+            }
+        }
         arr_index[i] = k;
         arr_cost[i] = k >= 0 ? c : INFINITY;
     }
@@ -556,6 +565,7 @@ public:
         memset(&stats, 0, sizeof(stats));
         if (const char* env = getenv("DABRY_FREE_CHUNK")) free_chunk = atoi(env);
         if (const char* env = getenv("DABRY_B200_WIDE_BATCH")) wide_batch = atoll(env);
+        if (const char* env = getenv("DABRY_B200_VERIFY_ARRIVALS")) verify_arrivals = atoi(env) != 0;
         if (const char* env = getenv("DABRY_B200_STREAM_UPLOAD")) stream_upload = atoi(env);
         times_h.assign(c.times, c.times + c.n_time);
         cfg.times = nullptr;
@@ -967,8 +977,24 @@ public:
         bind();
         if (int rc = ensure_aux(n_sites)) return rc;
         be.tic();
-        ArrivalPhase ap{S, d_arr_index, d_arr_cost};
+        ArrivalPhase ap{S, d_arr_index, d_arr_cost, 0};
         be.launch(n_sites, ap);
+        if (verify_arrivals) {
+            // DABRY_B200_VERIFY_ARRIVALS=1 (the test suites set it): the running arrival records against a fresh scan of
+            // every trajectory, the way check_solutions reads them (solver_ef.py:667-685)
+            std::vector<int32_t> idx_a(n_sites), idx_b(n_sites);
+            std::vector<double> cost_a(n_sites), cost_b(n_sites);
+            be.download(idx_a.data(), d_arr_index, sizeof(int32_t) * n_sites);
+            be.download(cost_a.data(), d_arr_cost, sizeof(double) * n_sites);
+            ArrivalPhase scan{S, d_arr_index, d_arr_cost, 1};
+            be.launch(n_sites, scan);
+            be.download(idx_b.data(), d_arr_index, sizeof(int32_t) * n_sites);
+            be.download(cost_b.data(), d_arr_cost, sizeof(double) * n_sites);
+            for (int64_t i = 0; i < n_sites; ++i)
+                if (idx_a[i] != idx_b[i] || !(cost_a[i] == cost_b[i]))
+                    return fail(DABRY_ERR_INVALID, "arrival records differ from a scan of the trajectories at slot " +
+                                                       std::to_string(i));
+        }
         // warp-level min reduction of the arrival cost, then of the slot among the minimisers (lowest slot wins)
         solution_cost = be.min_f64(d_arr_cost, n_sites);
         solution_site = -1;
@@ -1188,6 +1214,7 @@ private:
     // work items up to which the latency build of the arc kernels is launched.  The two builds differ in how ptxas
     // contracts multiply-adds (<= 1 ulp per operation); DABRY_B200_WIDE_BATCH=0 pins every batch to the lean build
     int64_t wide_batch = DABRY_WIDE_BATCH;
+    bool verify_arrivals = false;
     // streamed grid upload (set_flow_grid / pack_groups / integrate); DABRY_B200_STREAM_UPLOAD=0 disables it
     int stream_upload = 1;  // 0: never, 1: grids of 64 MB and more, 2: every eligible grid (tests)
     bool grid_pending = false;
@@ -1311,7 +1338,7 @@ private:
         be.free(s.check_next); be.free(s.depth); be.free(s.flags); be.free(s.parent_prev); be.free(s.parent_next);
         be.free(s.created_subframe); be.free(s.valid_first); be.free(s.valid_last); be.free(s.dyadic);
         be.free(s.next_nb); be.free(s.n_target_events); be.free(s.t_target_events); be.free(s.ivp_status);
-        be.free(s.arc_from); be.free(s.enter);
+        be.free(s.arc_from); be.free(s.enter); be.free(s.arr_index); be.free(s.arr_cost);
         be.free(s.carry_t); be.free(s.carry_h); be.free(s.carry_y); be.free(s.carry_f); be.free(s.carry_g);
         be.free(s.carry_eval_i);
     }
@@ -1351,6 +1378,7 @@ private:
         ok = ok && grow(S.dyadic, oc, cap, 1, 1) && grow(S.n_target_events, oc, cap, 1, 1);
         ok = ok && grow(S.t_target_events, oc, cap, 1, DABRY_MAX_TARGET_EVENTS) && grow(S.ivp_status, oc, cap, 1, 1);
         ok = ok && grow(S.arc_from, oc, cap, 1, 1) && grow(S.enter, oc, cap, 1, 1);
+        ok = ok && grow(S.arr_index, oc, cap, 1, 1) && grow(S.arr_cost, oc, cap, 1, 1);
         ok = ok && grow(S.carry_t, oc, cap, 1, 1) && grow(S.carry_h, oc, cap, 1, 1) && grow(S.carry_y, oc, cap, 1, 1);
         ok = ok && grow(S.carry_f, oc, cap, 1, 1) && grow(S.carry_g, oc, cap, 1, DABRY_MAX_EVENTS);
         ok = ok && grow(S.carry_eval_i, oc, cap, 1, 1);

@@ -69,6 +69,8 @@ struct SiteStore {
     double* t_target_events;    // [capacity][DABRY_MAX_TARGET_EVENTS]
     int32_t* ivp_status;        // status of the last solve_ivp call of the site (diagnostics)
     int32_t* arc_from;          // grid index the current integrate call started from (-1: nothing to do)
+    int32_t* arr_index;         // check_solutions, kept up to date by whoever writes a sample: grid index of the cheapest
+    double* arr_cost;           //   own sample strictly inside the target disc (-1 / +inf: none), and its cost
     Sample* enter;              // augmented state at the obstacle entry root, between the two integrate kernels
     // state of a free arc parked between two chunks of RK steps (IvpCarry)
     double* carry_t;
@@ -125,6 +127,8 @@ DABRY_HD void site_reset(const SiteStore& S, int s) {
     S.n_target_events[s] = 0;
     S.ivp_status[s] = 0;
     S.arc_from[s] = -1;
+    S.arr_index[s] = -1;
+    S.arr_cost[s] = INFINITY;
     // next_nb rows are filled with -1 when the storage is allocated; slots are never recycled
 }
 
@@ -163,6 +167,20 @@ struct FreeEvents {
     }
 };
 
+// check_solutions (solver_ef.py:667-685), the per-sample half: a sample strictly inside the target disc is a candidate
+// arrival, the cheapest one is kept.  Called by every writer of a sample (roots, children, both kinds of arcs) right
+// after the sample and its time are stored, so that no pass has to read the trajectories again.
+DABRY_HD void arrival_note(const ProblemDev& P, const SiteStore& S, int s, int k, double x0, double x1) {
+    const double d0 = x0 - P.x_target[0], d1 = x1 - P.x_target[1];
+    if (add_rn(mul_rn(d0, d0), mul_rn(d1, d1)) < P.target_radius_sq) {
+        const double c = site_cost_at(S, s, k);
+        if (S.arr_index[s] < 0 || c < S.arr_cost[s]) {
+            S.arr_index[s] = k;
+            S.arr_cost[s] = c;
+        }
+    }
+}
+
 struct NoEvents {
     DABRY_HD int count() const { return 0; }
     DABRY_HD bool terminal(int) const { return false; }
@@ -184,12 +202,14 @@ struct QuitEvent {
 };
 
 struct FreeSink {
+    const ProblemDev& P;
     const SiteStore& S;
     int site, slot0;  // grid index of linspace element 0
     DABRY_HD void emit(int j, double t, const double* y) {
         const int64_t o = S.at(site, slot0 + j);
         S.xp[o] = Sample{y[0], y[1], y[2], y[3]};
         S.tt[o] = t;  // the control stays NaN (free arc, solver_ef.py:500): the store is pre-filled, no write here
+        arrival_note(P, S, site, slot0 + j, y[0], y[1]);
     }
 };
 
@@ -206,6 +226,7 @@ struct ConstrSink {
         S.xp[o] = Sample{x[0], x[1], quiet_nan(), quiet_nan()};
         S.ctrl[o] = Control{u[0], u[1]};
         S.tt[o] = t;
+        arrival_note(P, S, site, slot0 + j, x[0], x[1]);
     }
 };
 
@@ -248,7 +269,7 @@ DABRY_HD void site_free_arc(const ProblemDev& P, const SiteStore& S, int s, int 
     const EvalGrid grid = make_eval_grid(S.times[idx0], S.times[index_t], n, 1);
     AugRhs<FK> rhs{P};
     FreeEvents ev{P, S, s};
-    FreeSink sink{S, s, idx0};
+    FreeSink sink{P, S, s, idx0};
     IvpResult<4> res;
 #if defined(__CUDA_ARCH__) && DABRY_K_IN_SHARED
     // the hot kernel keeps the stage values of the step in shared memory (rk45.cuh KShared): 32 KB per block
@@ -435,6 +456,7 @@ DABRY_HD void site_spawn(const SolverParams& C, const SiteStore& S, int a, int c
     S.tt[rc] = S.tt[ra];
     S.cost0[child] = 0.5 * (site_cost_at(S, a, index) + site_cost_at(S, b, index));
     S.index_t_init[child] = index;
+    arrival_note(problem(), S, child, index, 0.5 * (sa.x0 + sb.x0), 0.5 * (sa.x1 + sb.x1));  // the child's first sample
     S.check_next[child] = index;
     S.parent_prev[child] = a;
     S.parent_next[child] = b;

@@ -9,6 +9,11 @@ for p in (ROOT, os.path.join(ROOT, 'oracle'), os.path.join(ROOT, 'tests')):
         sys.path.insert(0, p)
 
 
+# every finish() of a test run checks the running arrival records (kept by the kernels that write samples) against a fresh
+# scan of the trajectories, the way check_solutions reads them; sub-processes of the sharding tests inherit it
+os.environ.setdefault('DABRY_B200_VERIFY_ARRIVALS', '1')
+
+
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (sm_100) and the built libdabry_b200.so')
 
