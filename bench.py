@@ -444,23 +444,23 @@ def main():
         bytes_per_step = BYTES_PER_STEP[(args.integrator, args.dtype)]
         ach = local_steps * bytes_per_step / (integ_total_ms * 1e-3) / 1e9
         # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the hot kernel at exactly this workload, from the
-        # ncu --set full capture summarised in profiles/r01_ncu_full_freearc_final.txt (0.394 GB read + 4.935 GB written)
-        traffic = 5.330e9 if (args.workload, args.roots_per_gpu, args.dtype, args.integrator, args.small) == \
+        # ncu --set full capture summarised in profiles/r01_ncu_full_freearc_final.txt (0.403 GB read + 4.970 GB written)
+        traffic = 5.373e9 if (args.workload, args.roots_per_gpu, args.dtype, args.integrator, args.small) == \
             ('era5', 1_250_000, 'f64', 'dopri5', False) else None
         roofline = {'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
                     'traffic': traffic, 'kernel': 'phase_kernel<FreeArcPhase<GRID>>', 'peak_source': peak_src,
                     'algorithmic_bytes_per_step': bytes_per_step,
                     'kernel_ms_per_launch': integ_total_ms / args.steps,
-                    'ncu_at_this_workload': {'l1_data_pipe_lsu_wavefronts_pct': 65.5, 'l1_lsu_writeback_pct': 45.3,
-                                             'fp64_pipe_active_pct': 44.5, 'issue_active_pct': 50.1,
-                                             'l1_hit_pct_global_loads': 96.5, 'l2_hit_pct': 80.9,
-                                             'active_lanes_per_warp_instruction': 23.1},
+                    'ncu_at_this_workload': {'l1_data_pipe_lsu_wavefronts_pct': 66.0, 'l1_lsu_writeback_pct': 45.7,
+                                             'fp64_pipe_active_pct': 44.3, 'issue_active_pct': 50.1,
+                                             'l1_hit_pct_global_loads': 96.4, 'l2_hit_pct': 81.0,
+                                             'active_lanes_per_warp_instruction': 23.2},
                     'note': 'algorithmic bytes (8 nodes x 6 scalars per RHS, zero reuse credit, + 32 B output) / measured '
                             'free-arc kernel time.  frac > 1: theta-sorted neighbours share grid cells, so the gather is served '
                             'by L1 (96 % of the node sectors) and DRAM traffic is 60x below the algorithmic bytes.  The unit that '
                             'binds is the L1 data stage: every 16-byte node piece is delivered to all 32 lanes (4 wavefronts per '
                             'LDG.128, broadcast or not) and the Runge-Kutta stage values cycle through local memory; ncu: L1 '
-                            'LSU data-pipe wavefronts 65.5 % of peak, fp64 pipe 44.5 %, issue slots 50.1 % - DESIGN.md 3 and 6'}
+                            'LSU data-pipe wavefronts 66 % of peak, fp64 pipe 44.3 %, issue slots 50.1 % - DESIGN.md 3 and 6'}
         if args.workload == 'gyre':
             roofline['note'] = 'analytic field: no gather, fp64-pipe bound; fraction of the gather roofline is nominal'
         line = {
