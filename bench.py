@@ -12,8 +12,9 @@ events, resampling scan, trim_distance, arrival-time argmin) of the named worklo
   gyre   BASELINE config 2 flow: analytic Gyre, 100 k roots per GPU, max_depth = 1 (fp64 pipe bound, no gather).
 
 `value`  : whole-job RK steps / device time, flow grid resident in HBM, roots generated on the device.
-`e2e`    : the same solve through the public API from HOST arrays: grid upload + repack, root costates upload,
-           solve, arrival arrays and the optimal trajectory read back - all inside the timed region.
+`e2e`    : the same solve through the public API from (page-locked) HOST arrays, everything inside the timed region: a
+           new solver per step, grid upload + repack (streamed in four groups of frames behind the free arcs), root
+           costates upload, solve, then the optimum, the slots of the solution sites and the optimal trajectory read back.
 `--impl reference`: the CPU oracle (oracle/solver_port.py: numpy + scipy solve_ivp like the reference) on a bounded
            sample of the same workload, all host cores (one process per core, independent theta_0 shards).
 """
