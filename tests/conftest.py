@@ -16,6 +16,14 @@ os.environ.setdefault('DABRY_B200_VERIFY_ARRIVALS', '1')
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (sm_100) and the built libdabry_b200.so')
+    # a fresh checkout has no built artefacts (they are git-ignored): build them once when nvcc is there
+    lib = os.path.join(ROOT, 'dabry_b200', 'libdabry_b200.so')
+    if not os.path.exists(lib):
+        import shutil
+        if shutil.which(os.environ.get('NVCC', 'nvcc')):
+            sys.path.insert(0, ROOT)
+            import __graft_entry__
+            __graft_entry__.build()
 
 
 def _cuda_available():
