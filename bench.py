@@ -1,22 +1,30 @@
 #!/usr/bin/env python
 """Benchmark of the extremal-field hot path (BASELINE.json: extremal-RK-steps/sec).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload era5|planar|gyre] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload era5|planar|gyre|regional] [--impl reference]
 
-One step = one full `SolverEFResampling` solve (setup, integration of every extremal over the whole horizon with
-events, resampling scan, trim_distance, arrival-time argmin) of the named workload on synthetic data:
+One step = one full `SolverEFResampling` / `SolverEFTrimming` solve (setup, integration of every extremal over the whole
+horizon with events, resampling scan, trimming, arrival-time argmin) of the named workload on synthetic data:
 
-  era5   (default) BASELINE config 4: ERA5-shaped spherical grid 1440 x 721 x 24, 1.25 M root extremals PER GPU
-         (10 M over 8 GPUs), max_depth = 1, DOPRI5 restated from scipy, fp64 grid + fp64 state.  Weak scaling.
-  planar BASELINE config 3: planar unsteady DiscreteFF 1024 x 1024 x 48, 2^19 roots per GPU, max_depth = 4.
-  gyre   BASELINE config 2 flow: analytic Gyre, 100 k roots per GPU, max_depth = 1 (fp64 pipe bound, no gather).
+  era5     (default) BASELINE config 4: ERA5-shaped spherical grid 1440 x 721 x 24, 1.25 M root extremals PER GPU
+           (10 M over 8 GPUs), max_depth = 1, DOPRI5 restated from scipy, fp64 grid + fp64 state.  Weak scaling.
+  planar   BASELINE config 3: planar unsteady DiscreteFF 1024 x 1024 x 48, 2^19 roots per GPU, max_depth = 4.
+  gyre     BASELINE config 2 flow: analytic Gyre, 100 k roots per GPU, max_depth = 1 (fp64 pipe bound, no gather).
+  regional BASELINE config 5: regional spherical grid + obstacle + penalty, SolverEFTrimming, 500 k roots per GPU.
 
-`value`  : whole-job RK steps / device time, flow grid resident in HBM, roots generated on the device.
-`e2e`    : the same solve through the public API from (page-locked) HOST arrays, everything inside the timed region: a
-           new solver per step, grid upload + repack (streamed in four groups of frames behind the free arcs), root
-           costates upload, solve, then the optimum, the slots of the solution sites and the optimal trajectory read back.
-`--impl reference`: the CPU oracle (oracle/solver_port.py: numpy + scipy solve_ivp like the reference) on a bounded
-           sample of the same workload, all host cores (one process per core, independent theta_0 shards).
+`value`    : whole-job RK steps / device time (CUDA events on the solver's stream around the solve - they bracket the
+             in-library NCCL exchanges too; max over ranks), flow grid resident in HBM, roots generated on the device.
+`e2e`      : the same solve through the public API from (page-locked) HOST arrays, everything inside the timed region: a
+             new solver per step, grid upload + repack (N = 1: streamed in groups of frames behind the free arcs;
+             N > 1: 1 / N of the grid per rank over PCIe, the rest from the peers by all-gather), root costates upload,
+             the sharded solve with its boundary exchange and global argmin, then the optimum, the slots of the solution
+             sites and the optimal trajectory read back.
+`roofline` : the unit that binds the hot kernel is the fp64 pipe (the gather is served by L1: DRAM traffic is 60x below
+             the algorithmic bytes), so the fraction is fp64 work / measured fp64 peak; SURVEY 8(d)'s byte figure is
+             kept beside it as `gather_equiv`.
+`secondary`: one short line per other BASELINE config (N = 1: configs 2, 3, 5; N > 1: config 5).
+`--impl reference`: the UNMODIFIED reference (baseline/_ref, dabry v1.1 through its own public API) on a bounded
+             sample of the same workload, one process per host core; the oracle port when baseline/_ref is absent.
 """
 import argparse
 import json
@@ -33,30 +41,38 @@ import numpy as np  # noqa: E402
 
 # RHS per step x 8 nodes x 6 scalars x bytes per scalar + 32 B of trajectory output
 BYTES_PER_STEP = {('dopri5', 'f64'): 2336, ('dopri5', 'f32'): 1184, ('rk4', 'f64'): 1568, ('rk4', 'f32'): 800}
-BYTES_PER_STEP_DOPRI5_F64 = 2336
 WORKLOADS = ('era5', 'planar', 'gyre', 'regional')
+REF_DIR = os.path.join(ROOT, 'baseline', '_ref')
 
 
-def build_problem(workload, small=False):
-    """(problem, total_duration, solver kwargs, description) - identical on every rank."""
+def build_problem(workload, small=False, api=None):
+    """(problem, total_duration, solver kwargs, description) - identical on every rank.  `api`: the module set to build
+    the problem with (default: this package's drop-in classes; the reference arm passes the reference's own)."""
     from dabry_b200 import synthetic
-    from dabry_b200.flowfield import DiscreteFF
-    from dabry_b200.misc import Coords
-    from dabry_b200.problem import NavigationProblem
+    if api is None:
+        from dabry_b200.flowfield import DiscreteFF
+        from dabry_b200.misc import Coords, Utils
+        from dabry_b200.problem import NavigationProblem
+        from dabry_b200.obstacle import CircleObs
+        from dabry_b200.penalty import CirclePenalty
+        grid_kw = dict(force_no_diff=True)  # derivatives are computed on the device
+    else:
+        DiscreteFF, Coords, Utils, NavigationProblem = api.DiscreteFF, api.Coords, api.Utils, api.NavigationProblem
+        CircleObs, CirclePenalty = api.CircleObs, api.CirclePenalty
+        grid_kw = {}
     if workload == 'era5':
         shape = (6, 180, 91) if small else (24, 1440, 721)
         sc = synthetic.era5_like(*shape)
-        ff = DiscreteFF(sc.values, sc.bounds, Coords.GCS, force_no_diff=True)
+        ff = DiscreteFF(sc.values, sc.bounds, Coords.GCS, **grid_kw)
         pb = NavigationProblem(ff, sc.x_init, sc.x_target, sc.srf, bl=sc.bl, tr=sc.tr, name='era5_like').rescale()
         # fixed horizon: 1.1 x the great-circle time at srf, in the rescaled clock (skips the host heuristics)
-        from dabry_b200.misc import Utils
         t_gc = Utils.distance(sc.x_init, sc.x_target, Coords.GCS) / sc.srf
         total = 1.1 * t_gc / (1. / (sc.srf / Utils.EARTH_RADIUS))
         return pb, total, dict(max_depth=1), 'era5_like %dx%dx%d gcs' % shape
     if workload == 'planar':
         shape = (6, 128, 128) if small else (48, 1024, 1024)
         sc = synthetic.planar_waves(*shape)
-        ff = DiscreteFF(sc.values, sc.bounds, Coords.CARTESIAN, force_no_diff=True)
+        ff = DiscreteFF(sc.values, sc.bounds, Coords.CARTESIAN, **grid_kw)
         pb = NavigationProblem(ff, sc.x_init, sc.x_target, sc.srf, bl=sc.bl, tr=sc.tr, name='planar_waves').rescale()
         # max_dist: 2^19 roots refine to ~1.0 M extremals at full size (SURVEY 8d config 3 asks for 0.9 - 1.1 M;
         # profiles/tune_planar_max_dist.py: 5e-5 -> 918 k, 3e-5 -> 1.077 M)
@@ -67,12 +83,9 @@ def build_problem(workload, small=False):
     if workload == 'regional':
         # BASELINE config 5: what NavigationProblem.from_database builds (0.5 deg box, 3-hourly frames over 48 h) plus
         # one circular obstacle and one circular penalty; SolverEFTrimming
-        from dabry_b200.obstacle import CircleObs
-        from dabry_b200.penalty import CirclePenalty
-        from dabry_b200.misc import Utils
         shape = (5, 41, 23) if small else (17, 181, 101)
         sc = synthetic.regional_constrained(*shape)
-        ff = DiscreteFF(sc.values, sc.bounds, Coords.GCS, force_no_diff=True)
+        ff = DiscreteFF(sc.values, sc.bounds, Coords.GCS, **grid_kw)
         obstacles = [CircleObs(np.array(c), float(r)) for c, r in sc.circle_obstacles]
         c, r, a = sc.circle_penalty
         pb = NavigationProblem(ff, sc.x_init, sc.x_target, sc.srf, bl=sc.bl, tr=sc.tr, obstacles=obstacles,
@@ -125,70 +138,196 @@ class ClockSampler(threading.Thread):
                 'reasons': sorted(reasons), 'samples': len(self.samples)}
 
 
-def measured_peak_gbs():
-    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+def _load_json(name):
     try:
-        with open(path) as f:
+        with open(os.path.join(ROOT, 'profiles', name)) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+def measured_hbm_gbs():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
             return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
     except Exception:
         return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
-# ---- CPU oracle legs ---------------------------------------------------------------------------------------
-_ORACLE_PROBLEM = {}
+def fp64_peak_tflops():
+    """fp64 pipe peak of a B200 (one DFMA = 2 flop), measured by profiles/microbench_fp64.cu - MEASURED_PEAKS.json has
+    no fp64 entry.  Fallback: NVIDIA's nominal 40 TFLOP/s."""
+    d = _load_json('r02_microbench_fp64.json')
+    if d and d.get('fp64_tflops_sustained'):
+        return float(d['fp64_tflops_sustained']), 'measured (profiles/microbench_fp64.cu -> profiles/r02_microbench_fp64.json)'
+    return 40.0, 'fallback (nominal B200 fp64)'
 
 
-def _oracle_problem(workload, small):
+def workload_signature(workload, roots_per_gpu, dtype, integrator, small):
+    return '%s|%d|%s|%s%s' % (workload, roots_per_gpu, dtype, integrator, '|small' if small else '')
+
+
+def roofline_for(sig, integrator, dtype, rk_steps_free, kernel_ms_total, n_launches, field_is_grid):
+    """fp64-pipe roofline of the free-arc kernel.  `achieved` = fp64 work of the timed launches / their measured
+    duration; the work per RK step is the ncu-derived constant of the capture of THIS workload
+    (profiles/r02_hot_kernel_counters.json, thread-level DFMA / DMUL / DADD of one launch / its RK steps) when there is
+    one, else the algorithmic estimate of SURVEY 8(d) - the source is stated.  Counters and DRAM traffic of a capture are
+    printed only for the workload they were captured on."""
+    caps = _load_json('r02_hot_kernel_counters.json') or {}
+    cap = caps.get(sig)
+    peak, peak_src = fp64_peak_tflops()
+    if cap:
+        flop_per_step = float(cap['fp64_flop_per_rk_step'])
+        ops_src = 'ncu capture of this workload (profiles/r02_hot_kernel_counters.json)'
+    else:
+        rhs = 6.02 if integrator == 'dopri5' else 4.
+        # per RHS ~170 mul/add (48 interpolation FMAs, weights, dynamics; sin, cos, sqrt, divisions expanded ~60) +
+        # ~200 per step of stage combinations, error norm and dense output; FMA-dominated: 1.6 flop per instruction
+        flop_per_step = (rhs * 170 + 200) * 1.6
+        ops_src = 'estimate (SURVEY 8d flop count); no ncu capture of this workload'
+    secs = kernel_ms_total * 1e-3
+    ach = rk_steps_free * flop_per_step / secs / 1e12
+    out = {'bound': 'fp64', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
+           'traffic': cap.get('dram_bytes_per_launch') if cap else None,
+           'kernel': 'phase_kernel<FreeArcPhase>', 'peak_source': peak_src,
+           'fp64_flop_per_rk_step': flop_per_step, 'flop_per_step_source': ops_src,
+           'rk_steps_free_per_solve': rk_steps_free / max(n_launches, 1),
+           'kernel_ms_per_solve': kernel_ms_total / max(n_launches, 1)}
+    if field_is_grid:
+        hbm, hbm_src = measured_hbm_gbs()
+        bps = BYTES_PER_STEP[(integrator, dtype)]
+        gbs = rk_steps_free * bps / secs / 1e9
+        out['gather_equiv'] = {'algorithmic_bytes_per_step': bps, 'gbs': gbs, 'hbm_peak_gbs': hbm, 'hbm_peak_source': hbm_src,
+                               'frac_of_hbm': gbs / hbm,
+                               'note': 'SURVEY 8(d) bytes with zero reuse credit; > 1 because theta-sorted neighbours share '
+                                       'grid cells and the gather is served by L1 - not the binding unit'}
+    if cap:
+        out['ncu_at_this_workload'] = cap.get('counters')
+    return out
+
+
+# ---- CPU legs: the unmodified reference (baseline/_ref) or the oracle port -----------------------------------------
+_CPU_PROBLEM = {}
+
+
+def reference_installed():
+    return os.path.isdir(os.path.join(REF_DIR, 'dabry'))
+
+
+def _reference_api():
+    """The reference's own modules from baseline/_ref, under the three import shims of SURVEY 8(c) (stub h5py / pygrib,
+    numpy.infty); its source is not touched."""
+    import types
+    import warnings
+    from types import SimpleNamespace
+    warnings.filterwarnings('ignore')
+    if not hasattr(np, 'infty'):
+        np.infty = np.inf
+    for missing in ('h5py', 'pygrib'):
+        if missing not in sys.modules:
+            try:
+                __import__(missing)
+            except ImportError:
+                sys.modules[missing] = types.ModuleType(missing)
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    import dabry.solver_ef as sef
+    from dabry.problem import NavigationProblem
+    from dabry.flowfield import DiscreteFF
+    from dabry.misc import Coords, Utils
+    from dabry.obstacle import CircleObs
+    from dabry.penalty import CirclePenalty
+    return SimpleNamespace(NavigationProblem=NavigationProblem, DiscreteFF=DiscreteFF, Coords=Coords, Utils=Utils,
+                           CircleObs=CircleObs, CirclePenalty=CirclePenalty, sef=sef)
+
+
+def _cpu_problem(workload, small, kind):
     """Per-process cache: the problem (grid + host derivatives) is built once per worker."""
-    key = (workload, small)
-    if key not in _ORACLE_PROBLEM:
+    key = (workload, small, kind)
+    if key not in _CPU_PROBLEM:
         import warnings
         warnings.filterwarnings('ignore')
-        pb, total, kw, _ = build_problem(workload, small)
-        inner = getattr(pb.model.ff, 'ff', None)
-        if inner is not None and getattr(inner, 'grad_values', 1) is None:
-            inner.compute_derivatives()  # the GPU arm differentiates on the device; the CPU oracle needs the host copy
-        _ORACLE_PROBLEM[key] = (pb, total)
-    return _ORACLE_PROBLEM[key]
+        if kind == 'reference':
+            api = _reference_api()
+            pb, total, kw, _ = build_problem(workload, small, api)
+            _CPU_PROBLEM[key] = (pb, total, kw, api)
+        else:
+            pb, total, kw, _ = build_problem(workload, small)
+            inner = getattr(pb.model.ff, 'ff', None)
+            if inner is not None and getattr(inner, 'grad_values', 1) is None:
+                inner.compute_derivatives()  # the GPU arm differentiates on the device; the CPU port needs the host copy
+            _CPU_PROBLEM[key] = (pb, total, kw, None)
+    return _CPU_PROBLEM[key]
 
 
-def _oracle_warm(args):
-    _oracle_problem(*args)
+def _cpu_warm(args):
+    _cpu_problem(*args)
     return 0
 
 
-def _oracle_shard(args):
-    workload, small, n_roots, lo, count = args
+class _IvpCounter:
+    def __init__(self, fn):
+        self.fn, self.steps = fn, 0
+
+    def __call__(self, *a, **k):
+        res = self.fn(*a, **k)
+        self.steps += (res.nfev - 2) // 6  # canonical count (SURVEY 8d)
+        return res
+
+
+def _cpu_shard(args):
+    workload, small, kind, n_roots, lo, count = args
+    pb, total, kw, api = _cpu_problem(workload, small, kind)
+    if kind == 'reference':
+        # the reference has no root_range: its sample is a fan of `count` roots over the whole circle, its own solver class
+        import contextlib
+        import io
+        sef = api.sef
+        kw = dict(kw)
+        cls = sef.SolverEFTrimming if kw.pop('trimming', False) else sef.SolverEFResampling
+        counter = _IvpCounter(sef.scitg.solve_ivp)
+        sef.scitg.solve_ivp = counter
+        try:
+            with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+                solver = cls(pb, total, n_costate_sectors=count, **kw)
+                t0 = time.perf_counter()
+                solver.solve()
+                dt = time.perf_counter() - t0
+        finally:
+            sef.scitg.solve_ivp = counter.fn
+        return counter.steps, dt, float('nan')
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     from solver_port import Port
-    pb, total = _oracle_problem(workload, small)
-    port = Port(pb, total, n_costate_sectors=n_roots, root_range=(lo, count), max_depth=1)
+    kw = dict(kw)
+    trimming = kw.pop('trimming', False)
+    port = Port(pb, total, n_costate_sectors=n_roots, root_range=(lo, count), **kw)
     t0 = time.perf_counter()
-    port.run_resampling()
+    port.run_trimming() if trimming else port.run_resampling()
     return port.n_rk, time.perf_counter() - t0, port.solution_cost
 
 
-class OraclePool:
+class CpuPool:
     """`cores` worker processes, each holding its own copy of the problem; a call times `sample_roots` extremals of
-    the workload's fan split into independent theta_0 shards, one per core."""
+    the workload split evenly over the cores."""
 
-    def __init__(self, workload, small, cores):
+    def __init__(self, workload, small, cores, kind):
         from multiprocessing import get_context
-        self.workload, self.small, self.cores = workload, small, cores
+        self.workload, self.small, self.cores, self.kind = workload, small, cores, kind
         self.pool = get_context('spawn').Pool(cores) if cores > 1 else None
         if self.pool:
-            self.pool.map(_oracle_warm, [(workload, small)] * cores, chunksize=1)
+            self.pool.map(_cpu_warm, [(workload, small, kind)] * cores, chunksize=1)
         else:
-            _oracle_problem(workload, small)
+            _cpu_problem(workload, small, kind)
 
     def run(self, n_roots, sample_roots):
-        per = max(1, sample_roots // self.cores)
+        per = max(2, sample_roots // self.cores)
         stride = max(1, n_roots // self.cores)
-        jobs = [(self.workload, self.small, n_roots, min(i * stride, n_roots - per), per) for i in range(self.cores)]
-        results = self.pool.map(_oracle_shard, jobs, chunksize=1) if self.pool else [_oracle_shard(jobs[0])]
+        jobs = [(self.workload, self.small, self.kind, n_roots, min(i * stride, n_roots - per), per)
+                for i in range(self.cores)]
+        results = self.pool.map(_cpu_shard, jobs, chunksize=1) if self.pool else [_cpu_shard(jobs[0])]
         steps = sum(r[0] for r in results)
         busy = max(r[1] for r in results)
-        return steps / busy, steps, busy
+        return steps / busy, steps, busy, per
 
     def close(self):
         if self.pool:
@@ -196,30 +335,43 @@ class OraclePool:
             self.pool.join()
 
 
-def oracle_throughput(workload, small, n_roots, sample_roots, cores):
-    pool = OraclePool(workload, small, cores)
+def cpu_cores():
+    """Host threads the CPU leg uses: every core, bounded by memory (a worker of the era5 workload holds ~3 GB)."""
+    cores = os.cpu_count() or 1
     try:
-        rate, steps, busy = pool.run(n_roots, sample_roots)
-    finally:
-        pool.close()
-    return rate, steps, busy, busy
+        with open('/proc/meminfo') as f:
+            kb = int([l for l in f if l.startswith('MemAvailable')][0].split()[1])
+        cores = max(1, min(cores, int(kb / 1e6 / 4)))
+    except Exception:
+        pass
+    return cores
+
+
+def cpu_sample_description(kind, sample, per, cores, n_roots):
+    if kind == 'reference':
+        return ('%d root extremals per step: %d solver instances of the unmodified reference (baseline/_ref, dabry v1.1), one '
+                'per core, each a fan of %d roots over the full circle of the same problem, full horizon' % (per * cores, cores, per))
+    return ('%d of %d root extremals (theta_0 shards of %d per core) through the oracle port, full horizon, per step'
+            % (per * cores, n_roots, per))
 
 
 def run_reference(args, rank, world):
-    """`--impl reference`: the reference's numpy/scipy CPU algorithm (oracle port) on all host cores."""
+    """`--impl reference`: the reference's own CPU implementation of the path on all host cores."""
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    kind = 'reference' if reference_installed() else 'port'
+    cores = cpu_cores()
     n_roots = args.roots_per_gpu * world
     n_runs = args.warmup + args.steps
-    # bounded sample: ~180 s of CPU work for the whole run at ~1 300 steps/s/core and ~109 steps per extremal
-    per_core = args.cpu_sample_roots // cores if args.cpu_sample_roots else int(max(2, min(100, 180. / n_runs * 1300 / 109)))
-    sample = per_core * cores
-    pool = OraclePool(args.workload, args.small, cores)
-    times, steps_tot = [], 0
+    # bounded sample: ~150 s of CPU work for the whole run; the reference does ~450 steps/s/core on a gridded spherical
+    # problem (SURVEY 6), the port ~1 300, an extremal takes ~110 steps
+    rate = 450. if kind == 'reference' else 1300.
+    per_core = args.cpu_sample_roots // cores if args.cpu_sample_roots else int(max(2, min(100, 150. / n_runs * rate / 110)))
+    pool = CpuPool(args.workload, args.small, cores, kind)
+    times, steps_tot, per = [], 0, per_core
     try:
         for i in range(n_runs):
-            rate, steps, busy = pool.run(n_roots, sample)
+            _, steps, busy, per = pool.run(n_roots, per_core * cores)
             if i >= args.warmup:
                 times.append(busy)
                 steps_tot += steps
@@ -232,9 +384,8 @@ def run_reference(args, rank, world):
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': args.workload + ('-small' if args.small else ''), 'roots_total': n_roots,
                    'parallelism': 'cpu x%d processes' % cores},
-        'cpu_baseline': {'value': value, 'unit': 'steps/s', 'cores': cores, 'kind': 'port',
-                         'sample': '%d of %d root extremals (theta_0 shards of %d per core), full horizon, per step'
-                                   % (sample, n_roots, per_core)},
+        'cpu_baseline': {'value': value, 'unit': 'steps/s', 'cores': cores, 'kind': kind,
+                         'sample': cpu_sample_description(kind, per * cores, per, cores, n_roots)},
         'e2e': {'value': value, 'unit': 'steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -242,6 +393,235 @@ def run_reference(args, rank, world):
 
 
 # ---- GPU arm -----------------------------------------------------------------------------------------------
+
+class Ctx:
+    """Process-group plumbing of one bench process."""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+        assert torch.cuda.is_available(), 'bench.py needs a CUDA device: dabry_b200 has no CPU execution path'
+        torch.cuda.set_device(self.local_rank)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+            dist.init_process_group('nccl', device_id=torch.device('cuda', self.local_rank))
+            self.dist = dist
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def _reduce(self, x, op):
+        if not self.dist:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device='cuda')
+        self.dist.all_reduce(t, op=getattr(self.dist.ReduceOp, op))
+        return float(t.item())
+
+    def reduce_max(self, x):
+        return self._reduce(x, 'MAX')
+
+    def reduce_min(self, x):
+        return self._reduce(x, 'MIN')
+
+    def reduce_sum(self, x):
+        return self._reduce(x, 'SUM')
+
+
+class Workload:
+    """One BASELINE config on this rank: problem, sharding, solver factory, the two timed arms."""
+
+    def __init__(self, ctx, name, roots_per_gpu, dtype, integrator, small, shard_block):
+        from dabry_b200 import _native as nat
+        from dabry_b200.distributed import shard_range, ShardedResampling, ShardedTrimming
+        from dabry_b200.solver_ef import SolverEFResampling, SolverEFTrimming
+        self.ctx, self.name, self.dtype, self.integrator, self.small = ctx, name, dtype, integrator, small
+        self.nat = nat
+        self.pb, self.total, kw, self.descr = build_problem(name, small)
+        self.trimming = bool(kw.pop('trimming', False))
+        self.kw = kw
+        self.solver_cls = SolverEFTrimming if self.trimming else SolverEFResampling
+        self.runner_cls = ShardedTrimming if self.trimming else ShardedResampling
+        self.variant = nat.TRIMMING if self.trimming else nat.RESAMPLING
+        self.roots_per_gpu = roots_per_gpu
+        self.n_roots = roots_per_gpu * ctx.world
+        self.shard_block = shard_block if ctx.world > 1 else 0
+        if self.shard_block and roots_per_gpu % self.shard_block != 0:
+            self.shard_block = 0
+        self.shard = (ctx.rank, ctx.world, self.shard_block) if self.shard_block else None
+        self.root_range = shard_range(self.n_roots, ctx.rank, ctx.world) if ctx.world > 1 and self.shard is None else None
+        self.count = self.n_roots // ctx.world if self.shard else (self.root_range[1] if self.root_range else self.n_roots)
+        cap_factor = 1.02 if kw.get('max_depth', 1) == 1 else 2.5
+        self.max_sites = int(self.count * cap_factor) + 4096
+        inner = getattr(self.pb.model.ff, 'ff', self.pb.model.ff)
+        self.grid = inner if hasattr(inner, 'values') else None
+
+    def signature(self):
+        return workload_signature(self.name, self.roots_per_gpu, self.dtype, self.integrator, self.small)
+
+    def make_solver(self, device_roots, **extra):
+        args_ = dict(n_costate_sectors=self.n_roots, device=self.ctx.local_rank, max_sites=self.max_sites,
+                     device_roots=device_roots, dtype=self.dtype, integrator=self.integrator)
+        args_.update(self.kw)
+        args_.update(extra)
+        return self.solver_cls(self.pb, self.total, **args_)
+
+    def make_runner(self, device_roots):
+        """The sharded runner (every N): its solver calls dabry_solve_sharded, which is dabry_solve on one GPU."""
+        return self.runner_cls(lambda **k: self.make_solver(device_roots, **k), self.n_roots, device=self.ctx.local_rank,
+                               block=self.shard_block or None)
+
+    # ---- resident arm: grid uploaded once, K timed solves ----
+    def resident(self, steps, warmup, keep=False):
+        ctx, torch = self.ctx, self.ctx.torch
+        runner = self.make_runner(device_roots=True)
+        solver = runner.solver
+        handle = solver._ensure_handle()
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')  # > 126 MB L2
+
+        def one_step():
+            flush.zero_()  # L2 flush between iterations
+            torch.cuda.synchronize()
+            runner.solve(fetch=False)
+            return handle.stats()
+
+        for _ in range(warmup):
+            one_step()
+        ctx.barrier()
+        sampler = ClockSampler(ctx.local_rank)
+        sampler.start()
+        base = handle.stats()
+        dev_ms, integ_ms, steps_rk, steps_free = [], [], [], []
+        phases = {}
+        t_wall = time.perf_counter()
+        for _ in range(steps):
+            st = one_step()
+            dev_ms.append(st['ms_total'])
+            integ_ms.append(st['ms_integrate'])
+            steps_rk.append(st['rk_steps'])
+            steps_free.append(st['rk_steps_free'])
+            for k in ('ms_integrate', 'ms_obstacle', 'ms_resample', 'ms_trim', 'ms_arrival', 'ms_comm', 'ms_total'):
+                phases[k] = phases.get(k, 0.) + st[k] / steps
+        ctx.barrier()
+        wall_ms = 1e3 * (time.perf_counter() - t_wall)
+        clocks = sampler.stop()
+        last = handle.stats()
+        out = {
+            'launches': int(last['kernel_launches'] - base['kernel_launches']),
+            'n_sites': int(last['n_sites']),
+            'cost_local': handle.solution()[1],
+            'cost_global': runner.global_cost,
+            'owner_rank': runner.owner_rank,
+            # CUDA events on the solver's stream around dabry_solve_sharded (they bracket the NCCL exchanges, which are
+            # enqueued on the same stream); the slowest rank counts
+            'dev_ms_total': ctx.reduce_max(float(sum(dev_ms))),
+            'wall_ms_total': ctx.reduce_max(wall_ms),
+            'total_steps': ctx.reduce_sum(float(sum(steps_rk))),
+            'local_steps': float(sum(steps_rk)), 'local_steps_free': float(sum(steps_free)),
+            'integ_ms_total': float(sum(integ_ms)),
+            'phases': {k: round(v, 3) for k, v in phases.items()}, 'clocks': clocks,
+        }
+        del flush
+        if keep:
+            out['runner'] = runner
+        else:
+            solver.close()
+        return out
+
+    # ---- end-to-end arm: public API from host arrays, every step ----
+    def e2e(self, steps):
+        ctx, nat = self.ctx, self.nat
+        h2d = int((self.grid.values.nbytes // ctx.world if self.grid is not None else 0) + 16 * self.count)
+        if self.grid is not None and hasattr(self.grid, 'pin_memory'):
+            self.grid.pin_memory()  # the step's input (the flow samples) lives in pinned host memory
+
+        def e2e_step():
+            runner = self.make_runner(device_roots=False)
+            runner.solve(fetch=True)
+            s = runner.solver
+            cost = runner.global_cost
+            # what is read back: the optimum (16 B), the slots of the solution sites (compacted on the device) and the
+            # optimal trajectory; the per-site arrival arrays stay on the device until someone asks for them
+            d2h = 16 + 4 * int(s._solution_slots.shape[0])
+            if s.solution_site is not None:
+                traj = s.solution_site.traj
+                d2h += int(traj.states.nbytes + traj.times.nbytes + traj.costates.nbytes)
+            rk = s.native_stats()['rk_steps']
+            s.close()
+            return cost, rk, d2h
+
+        e2e_step()
+        ctx.barrier()
+        t0 = time.perf_counter()
+        rk_sum, d2h, cost = 0, 0, float('nan')
+        step_ms, step_calls = [], []
+        for _ in range(steps):
+            nat.CALL_TIMES = {}
+            t1 = time.perf_counter()
+            cost, rk, d2h = e2e_step()
+            rk_sum += rk
+            step_ms.append(round(1e3 * (time.perf_counter() - t1), 2))
+            step_calls.append({k[6:]: round(1e3 * v, 2) for k, v in nat.CALL_TIMES.items() if v > 2e-4})
+        nat.CALL_TIMES = None
+        ctx.barrier()
+        secs = ctx.reduce_max(time.perf_counter() - t0)
+        return {'value': ctx.reduce_sum(float(rk_sum)) / secs, 'unit': 'steps/s', 'h2d_bytes_per_step': h2d,
+                'd2h_bytes_per_step': int(d2h), 'steps': steps, 'ms_per_step': 1e3 * secs / steps,
+                'ms_each_step_rank0': step_ms, 'native_ms_slowest_step_rank0': step_calls[int(np.argmax(step_ms))],
+                'path': 'ShardedResampling/ShardedTrimming -> dabry_solve_sharded (in-library NCCL)' if ctx.world > 1
+                        else 'SolverEF*.solve -> dabry_solve',
+                'arrival_cost': None if np.isnan(cost) else cost}
+
+    # ---- driver-visible correctness of the sharding ----
+    def shard_check(self, runner, sample=1000):
+        """Every rank re-solves a sample of its NEIGHBOUR's roots on its own GPU (a plain single-handle solve of the ring
+        range) and compares them bit for bit with what the neighbour holds from the timed sharded solve."""
+        ctx, torch, dist = self.ctx, self.ctx.torch, self.ctx.dist
+        if ctx.world == 1:
+            return 'n/a (1 GPU)'
+        if self.trimming or self.kw.get('max_depth', 1) != 1:
+            return 'skipped (children and trimming depend on the whole front)'
+        n = min(sample, self.shard_block or self.count)
+        mine = runner.solver._handle
+        rec = mine.sites(0, n)
+        own = np.concatenate((mine.trajs(0, n, want=('states',))['states'].reshape(n, -1),
+                              rec['n_samples'][:, None].astype(float), rec['closure'][:, None].astype(float)), axis=1)
+        t_own = torch.from_numpy(np.ascontiguousarray(own)).cuda()
+        gathered = [torch.empty_like(t_own) for _ in range(ctx.world)]
+        dist.all_gather(gathered, t_own)
+        nb = (ctx.rank + 1) % ctx.world
+        first = nb * self.shard_block if self.shard_block else self.root_range_of(nb)[0]
+        s = self.make_solver(device_roots=True, root_range=(first, n), max_sites=n + 4096)
+        s.solve()
+        h = s._handle
+        rec2 = h.sites(0, n)
+        again = np.concatenate((h.trajs(0, n, want=('states',))['states'].reshape(n, -1),
+                                rec2['n_samples'][:, None].astype(float), rec2['closure'][:, None].astype(float)), axis=1)
+        s.close()
+        theirs = gathered[nb].cpu().numpy()
+        same = np.array_equal(again.view(np.uint64), theirs.view(np.uint64))  # bit for bit, NaN padding included
+        ok = ctx.reduce_min(1. if same else 0.)
+        return 'ok' if ok == 1. else 'MISMATCH'
+
+    def root_range_of(self, rank):
+        from dabry_b200.distributed import shard_range
+        return shard_range(self.n_roots, rank, self.ctx.world)
+
+
+def short_line(w, r):
+    return {'workload': w.name, 'flow': w.descr, 'solver': w.solver_cls.__name__, 'roots_per_gpu': w.roots_per_gpu,
+            'integrator': w.integrator, 'sites_rank0': r['n_sites'],
+            'value': r['total_steps'] / (r['dev_ms_total'] * 1e-3), 'unit': 'steps/s',
+            'ms_per_step': None, 'phase_ms_rank0': r['phases'], 'gpu_launches': r['launches'],
+            'arrival_cost_global': None if np.isnan(r['cost_global']) else r['cost_global']}
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -255,6 +635,7 @@ def main():
     ap.add_argument('--cpu-sample-roots', type=int, default=0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-secondary', action='store_true')
     ap.add_argument('--shard-block', type=int, default=5000,
                     help='N > 1: block-cyclic theta_0 sharding with this many roots per block (0: contiguous ranges)')
     ap.add_argument('--dtype', choices=('f64', 'f32'), default='f64', help="f32 = flow grid stored in fp32 (tolerance 1e-4)")
@@ -262,227 +643,89 @@ def main():
     args = ap.parse_args()
     if args.roots_per_gpu <= 0:
         args.roots_per_gpu = default_roots(args.workload)
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     if args.impl == 'reference':
-        run_reference(args, rank, world)
+        run_reference(args, int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1')))
         return
     if args.warmup < 3:
         print('note: fewer than 3 warm-up steps requested', file=sys.stderr)
 
-    import torch
-    import torch.distributed as dist
-    assert torch.cuda.is_available(), 'bench.py needs a CUDA device: dabry_b200 has no CPU execution path'
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    ctx = Ctx()
+    rank, world = ctx.rank, ctx.world
+    w = Workload(ctx, args.workload, args.roots_per_gpu, args.dtype, args.integrator, args.small, args.shard_block)
+    r = w.resident(args.steps, args.warmup, keep=True)
+    check = w.shard_check(r['runner'])
+    r.pop('runner').solver.close()
+    value = r['total_steps'] / (r['dev_ms_total'] * 1e-3)
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    from dabry_b200 import _native as nat
-    from dabry_b200.distributed import shard_range
-    from dabry_b200.solver_ef import SolverEFResampling, SolverEFTrimming
-
-    pb, total, kw, descr = build_problem(args.workload, args.small)
-    trimming = bool(kw.pop('trimming', False))
-    solver_cls = SolverEFTrimming if trimming else SolverEFResampling
-    variant = nat.TRIMMING if trimming else nat.RESAMPLING
-    n_roots = args.roots_per_gpu * world
-    shard = (rank, world, args.shard_block) if world > 1 and args.shard_block > 0 else None
-    root_range = shard_range(n_roots, rank, world) if world > 1 and shard is None else None
-    count = n_roots // world if shard else (root_range[1] if root_range else n_roots)
-    cap_factor = 1.02 if kw.get('max_depth', 1) == 1 else 2.5
-    max_sites = int(count * cap_factor) + 4096
-
-    def make_solver(device_roots, **extra):
-        args_ = dict(n_costate_sectors=n_roots, root_range=root_range, shard=shard, device=local_rank,
-                     max_sites=max_sites, device_roots=device_roots, dtype=args.dtype, integrator=args.integrator)
-        args_.update(kw)
-        args_.update(extra)
-        return solver_cls(pb, total, **args_)
-
-    # ---- resident arm: grid uploaded once, K timed solves ----
-    from dabry_b200.distributed import ShardedResampling, ShardedTrimming
-    if world == 1:
-        # single process: ShardedResampling needs a process group only for its collectives
-        class _Solo:
-            def __init__(self, solver):
-                self.solver = solver
-
-            def solve(self, fetch=True):
-                h = self.solver._ensure_handle()
-                h.call('dabry_solve', variant, nat.dptr(self.solver._root_costates()))
-                return self
-        runner = _Solo(make_solver(device_roots=True))
-    else:
-        runner = (ShardedTrimming if trimming else ShardedResampling)(
-            lambda **k: make_solver(device_roots=True), n_roots, device=local_rank, block=args.shard_block or None)
-    solver = runner.solver
-    handle = solver._ensure_handle()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')  # > 126 MB L2
-
-    def one_step():
-        flush.zero_()  # L2 flush between iterations
-        torch.cuda.synchronize()
-        runner.solve(fetch=False)
-        after = handle.stats()
-        # dabry_solve times itself (ms_total); the split-step path of the sharded run is timed phase by phase
-        if world > 1:
-            after['ms_total'] = sum(after[k] for k in ('ms_integrate', 'ms_obstacle', 'ms_resample', 'ms_trim',
-                                                       'ms_arrival'))
-        return after
-
-    for _ in range(args.warmup):
-        one_step()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    base = handle.stats()
-    dev_ms, integ_ms, steps_rk = [], [], []
-    phases = {}
-    t_wall = time.perf_counter()
-    for _ in range(args.steps):
-        st = one_step()
-        dev_ms.append(st['ms_total'])
-        integ_ms.append(st['ms_integrate'])
-        steps_rk.append(st['rk_steps'])
-        for k in ('ms_integrate', 'ms_obstacle', 'ms_resample', 'ms_trim', 'ms_arrival', 'ms_total'):
-            phases[k] = phases.get(k, 0.) + st[k] / args.steps
-    barrier()
-    wall_ms = 1e3 * (time.perf_counter() - t_wall)
-    clocks = sampler.stop()
-    last = handle.stats()
-    launches = int(last['kernel_launches'] - base['kernel_launches'])
-    n_sites = int(last['n_sites'])
-    cost_resident = handle.solution()[1]
-    cost_global = getattr(runner, 'global_cost', cost_resident) if world > 1 else cost_resident
-
-    def reduce_max(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device='cuda')
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def reduce_sum(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device='cuda')
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
-    total_wall_ms = reduce_max(wall_ms)
-    # N = 1: CUDA events around dabry_solve on the library's stream.  N > 1: the bracket between the two barriers
-    # (it contains the ring-boundary exchange and the arrival all_reduce, which no single-stream event pair sees)
-    total_dev_ms = reduce_max(float(sum(dev_ms))) if world == 1 else total_wall_ms
-    total_steps = reduce_sum(float(sum(steps_rk)))
-    value = total_steps / (total_dev_ms * 1e-3)
-    integ_total_ms = float(sum(integ_ms))
-    local_steps = float(sum(steps_rk))
-    solver.close()
-    del flush
-
-    # ---- end-to-end arm: public API from host arrays, every step ----
     e2e = None
     if not args.no_e2e:
-        inner = getattr(pb.model.ff, 'ff', pb.model.ff)
-        h2d = int((inner.values.nbytes if hasattr(inner, 'values') else 0) + 16 * count)
-        if hasattr(inner, 'pin_memory'):
-            inner.pin_memory()  # the step's input (the flow samples) lives in pinned host memory, as the contract asks
+        e2e = w.e2e(max(1, min(args.steps, 3)))
 
-        def e2e_step():
-            s = make_solver(device_roots=False)
-            s.solve()
-            cost = s.solution_cost
-            # what is read back: the optimum (16 B), the slots of the solution sites (compacted on the device) and the
-            # optimal trajectory; the per-site arrival arrays stay on the device until someone asks for them
-            d2h = 16 + 4 * int(s._solution_slots.shape[0])
-            if s.solution_site is not None:
-                traj = s.solution_site.traj
-                d2h += int(traj.states.nbytes + traj.times.nbytes + traj.costates.nbytes)
-            rk = s.native_stats()['rk_steps']
-            s.close()
-            return cost, rk, d2h
-
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        rk_sum, d2h = 0, 0
-        n_e2e = max(1, min(args.steps, 3))
-        step_ms, step_calls = [], []
-        for _ in range(n_e2e):
-            nat.CALL_TIMES = {}
-            t1 = time.perf_counter()
-            cost_e2e, rk, d2h = e2e_step()
-            rk_sum += rk
-            step_ms.append(round(1e3 * (time.perf_counter() - t1), 2))
-            step_calls.append({k[6:]: round(1e3 * v, 2) for k, v in nat.CALL_TIMES.items() if v > 2e-4})
-        nat.CALL_TIMES = None
-        barrier()
-        e2e_s = reduce_max(time.perf_counter() - t0)
-        e2e = {'value': reduce_sum(float(rk_sum)) / e2e_s, 'unit': 'steps/s', 'h2d_bytes_per_step': h2d,
-               'd2h_bytes_per_step': int(d2h), 'steps': n_e2e, 'ms_per_step': 1e3 * e2e_s / n_e2e, 'ms_each_step_rank0': step_ms, 'native_ms_slowest_step_rank0': step_calls[int(np.argmax(step_ms))],
-               'arrival_cost': None if np.isnan(cost_e2e) else cost_e2e}
+    # ---- the other BASELINE configs, short (same build, same process) ----
+    secondary = None
+    if not args.no_secondary and not args.small:
+        secondary = {}
+        others = [('gyre', 'rk4'), ('planar', 'dopri5'), ('regional', 'dopri5')] if world == 1 else [('regional', 'dopri5')]
+        for name, integ in others:
+            if name == args.workload:
+                continue
+            try:
+                w2 = Workload(ctx, name, default_roots(name), 'f64', integ, False, args.shard_block)
+                r2 = w2.resident(3, 2)
+                line2 = short_line(w2, r2)
+                line2['ms_per_step'] = r2['dev_ms_total'] / 3
+                line2['wall_ms_per_step'] = r2['wall_ms_total'] / 3
+                secondary[name + ('_rk4' if integ == 'rk4' else '')] = line2
+                del w2
+            except Exception as exc:  # a secondary line must not take the headline down
+                secondary[name] = {'error': repr(exc)[:300]}
 
     # ---- CPU baseline (rank 0, N = 1) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = 1
-        sample = args.cpu_sample_roots if args.cpu_sample_roots else 160
-        rate, steps, busy, _ = oracle_throughput(args.workload, args.small, n_roots, sample, cores)
-        cpu = {'value': rate, 'unit': 'steps/s', 'cores': cores, 'kind': 'port',
-               'sample': '%d of %d root extremals, full horizon (%d RK steps in %.1f s); %d host cores present'
-                         % (sample, n_roots, steps, busy, os.cpu_count() or 1)}
+        kind = 'reference' if reference_installed() else 'port'
+        cores = cpu_cores()
+        per_core = (args.cpu_sample_roots // cores) if args.cpu_sample_roots else (16 if kind == 'reference' else 48)
+        pool = CpuPool(args.workload, args.small, cores, kind)
+        try:
+            rate, steps, busy, per = pool.run(w.n_roots, per_core * cores)
+        finally:
+            pool.close()
+        cpu = {'value': rate, 'unit': 'steps/s', 'cores': cores, 'kind': kind,
+               'sample': cpu_sample_description(kind, per * cores, per, cores, w.n_roots)
+                         + ' (%d RK steps in %.1f s; %d host cores present)' % (steps, busy, os.cpu_count() or 1)}
 
     if rank == 0:
-        peak, peak_src = measured_peak_gbs()
-        bytes_per_step = BYTES_PER_STEP[(args.integrator, args.dtype)]
-        ach = local_steps * bytes_per_step / (integ_total_ms * 1e-3) / 1e9
-        # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the hot kernel at exactly this workload, from the
-        # ncu --set full capture summarised in profiles/r01_ncu_full_freearc_final.txt (0.403 GB read + 4.970 GB written)
-        traffic = 5.373e9 if (args.workload, args.roots_per_gpu, args.dtype, args.integrator, args.small) == \
-            ('era5', 1_250_000, 'f64', 'dopri5', False) else None
-        roofline = {'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
-                    'traffic': traffic, 'kernel': 'phase_kernel<FreeArcPhase<GRID>>', 'peak_source': peak_src,
-                    'algorithmic_bytes_per_step': bytes_per_step,
-                    'kernel_ms_per_launch': integ_total_ms / args.steps,
-                    'ncu_at_this_workload': {'l1_data_pipe_lsu_wavefronts_pct': 66.0, 'l1_lsu_writeback_pct': 45.7,
-                                             'fp64_pipe_active_pct': 44.3, 'issue_active_pct': 50.1,
-                                             'l1_hit_pct_global_loads': 96.4, 'l2_hit_pct': 81.0,
-                                             'active_lanes_per_warp_instruction': 23.2},
-                    'note': 'algorithmic bytes (8 nodes x 6 scalars per RHS, zero reuse credit, + 32 B output) / measured '
-                            'free-arc kernel time.  frac > 1: theta-sorted neighbours share grid cells, so the gather is served '
-                            'by L1 (96 % of the node sectors) and DRAM traffic is 60x below the algorithmic bytes.  The unit that '
-                            'binds is the L1 data stage: every 16-byte node piece is delivered to all 32 lanes (4 wavefronts per '
-                            'LDG.128, broadcast or not) and the Runge-Kutta stage values cycle through local memory; ncu: L1 '
-                            'LSU data-pipe wavefronts 66 % of peak, fp64 pipe 44.3 %, issue slots 50.1 % - DESIGN.md 3 and 6'}
-        if args.workload == 'gyre':
-            roofline['note'] = 'analytic field: no gather, fp64-pipe bound; fraction of the gather roofline is nominal'
+        roofline = roofline_for(w.signature(), args.integrator, args.dtype, r['local_steps_free'], r['integ_ms_total'],
+                                args.steps, w.grid is not None)
+        cost_local, cost_global = r['cost_local'], r['cost_global']
         line = {
             'metric': 'extremal_rk_steps_per_sec', 'value': value, 'unit': 'steps/s', 'n_gpus': world,
-            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_dev_ms / args.steps,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64' if args.dtype == 'f64' else 'f64 state / f32 grid', 'data': 'synthetic',
-            'config': {'workload': args.workload + ('-small' if args.small else ''), 'flow': descr,
-                       'roots_per_gpu': args.roots_per_gpu, 'roots_total': n_roots, 'sites_rank0': n_sites,
-                       'integrator': 'dopri5_scipy' if args.integrator == 'dopri5' else 'rk4_fixed', 'n_time': 100, 'max_depth': kw.get('max_depth'), 'solver': solver_cls.__name__,
-                       'parallelism': 'theta0-shard x%d (%s)' % (world, 'block-cyclic, %d roots per block' % args.shard_block
-                                                                 if shard else 'contiguous'), 'l2': 'flushed between steps (256 MiB write)',
-                       'timing': 'cuda events on the library stream' if world == 1 else 'barrier-bracketed wall clock, max over ranks',
-                       'wall_ms_per_step': total_wall_ms / args.steps,
-                       'phase_ms_rank0': {k: round(v, 3) for k, v in phases.items()},
-                       'arrival_cost_rank0': None if np.isnan(cost_resident) else cost_resident,
-                       'arrival_cost_global': None if np.isnan(cost_global) else cost_global},
-            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': r['dev_ms_total'] / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f64' if args.dtype == 'f64' else 'f64 state / f32 grid', 'data': 'synthetic',
+            'config': {'workload': args.workload + ('-small' if args.small else ''), 'flow': w.descr,
+                       'roots_per_gpu': args.roots_per_gpu, 'roots_total': w.n_roots, 'sites_rank0': r['n_sites'],
+                       'integrator': 'dopri5_scipy' if args.integrator == 'dopri5' else 'rk4_fixed', 'n_time': 100,
+                       'max_depth': w.kw.get('max_depth'), 'solver': w.solver_cls.__name__,
+                       'parallelism': 'theta0-shard x%d (%s)' % (world, 'block-cyclic, %d roots per block' % w.shard_block
+                                                                 if w.shard else 'contiguous'),
+                       'collectives': 'in-library NCCL on the solver stream (ring send/recv, all-gather argmin)' if world > 1 else None,
+                       'l2': 'flushed between steps (256 MiB write)',
+                       'timing': 'cuda events on the solver stream around the (sharded) solve, max over ranks',
+                       'wall_ms_per_step': r['wall_ms_total'] / args.steps,
+                       'phase_ms_rank0': r['phases'],
+                       'arrival_cost_rank0': None if np.isnan(cost_local) else cost_local,
+                       'arrival_cost_global': None if np.isnan(cost_global) else cost_global,
+                       'owner_rank': r['owner_rank']},
+            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': r['launches'], 'clocks': r['clocks'],
+            'shard_check': check, 'secondary': secondary,
         }
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    if ctx.dist:
+        from dabry_b200.distributed import close_comms
+        close_comms()
+        ctx.dist.destroy_process_group()
 
 
 if __name__ == '__main__':

@@ -22,8 +22,9 @@ def unwrap_flow(ff):
     return w, ff
 
 
-def apply_flow(handle, ff):
-    """Upload the flow field of a problem into a native handle."""
+def apply_flow(handle, ff, shared=False):
+    """Upload the flow field of a problem into a native handle.  shared: every rank of the handle's communicator holds
+    the same grid - each uploads its share and the peers exchange the rest (dabry_set_flow_grid_shared)."""
     wrapper, inner = unwrap_flow(ff)
     if isinstance(inner, DiscreteFF):
         values = nat.f64(inner.values)
@@ -38,8 +39,12 @@ def apply_flow(handle, ff):
         b = np.asarray(inner.bounds, dtype=float)
         lo = nat.f64(np.concatenate(((0.,), b[:, 0])) if not unsteady else b[:, 0])
         hi = nat.f64(np.concatenate(((0.,), b[:, 1])) if not unsteady else b[:, 1])
-        handle.call('dabry_set_flow_grid', nat.dptr(values), nat.dptr(grad), nt, nx, ny, 1 if unsteady else 0,
-                    nat.dptr(lo), nat.dptr(hi), C.byref(wrapper))
+        if shared and grad is None:
+            handle.call('dabry_set_flow_grid_shared', nat.dptr(values), nt, nx, ny, 1 if unsteady else 0,
+                        nat.dptr(lo), nat.dptr(hi), C.byref(wrapper))
+        else:
+            handle.call('dabry_set_flow_grid', nat.dptr(values), nat.dptr(grad), nt, nx, ny, 1 if unsteady else 0,
+                        nat.dptr(lo), nat.dptr(hi), C.byref(wrapper))
         # a page-locked array is uploaded in the background (streamed upload): it must outlive the first solve
         handle._keep = tuple(handle._keep) + (values,)
         return

@@ -11,7 +11,8 @@ import os
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
+COMM_ID_BYTES = 128
 MAX_TARGET_EVENTS = 4
 
 SIMPLE, RESAMPLING, TRIMMING = 0, 1, 2
@@ -75,7 +76,8 @@ class Stats(C.Structure):
                 ('kernel_launches', C.c_uint64), ('n_sites', C.c_int64), ('capacity', C.c_int64),
                 ('rounds', C.c_int32), ('pad_', C.c_int32), ('ms_integrate', C.c_double),
                 ('ms_resample', C.c_double), ('ms_trim', C.c_double), ('ms_arrival', C.c_double),
-                ('ms_total', C.c_double), ('ms_upload', C.c_double), ('ms_obstacle', C.c_double)]
+                ('ms_total', C.c_double), ('ms_upload', C.c_double), ('ms_obstacle', C.c_double),
+                ('ms_comm', C.c_double), ('rk_steps_free', C.c_uint64)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_ if name != 'pad_'}
@@ -126,6 +128,15 @@ SIGNATURES = {
     'dabry_import_boundary_device': (C.c_int, [_H, C.c_void_p]),
     'dabry_get_cost_map_device': (C.c_int, [_H, C.c_int32, C.c_void_p]),
     'dabry_set_cost_map_device': (C.c_int, [_H, C.c_void_p]),
+    'dabry_comm_unique_id': (C.c_int, [C.c_void_p]),
+    'dabry_comm_create': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
+    'dabry_comm_destroy': (None, [C.c_void_p]),
+    'dabry_comm_last_error': (C.c_char_p, []),
+    'dabry_attach_comm': (C.c_int, [_H, C.c_void_p]),
+    'dabry_set_flow_grid_shared': (C.c_int, [_H, c_double_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_double_p,
+                                             c_double_p, C.POINTER(Wrapper)]),
+    'dabry_solve_sharded': (C.c_int, [_H, C.c_int32, c_double_p]),
+    'dabry_get_global_solution': (C.c_int, [_H, c_double_p, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]),
     'dabry_eval_rhs': (C.c_int, [_H, C.c_int64, c_double_p, c_double_p, c_double_p]),
     'dabry_eval_flow': (C.c_int, [_H, C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p]),
 }
@@ -222,6 +233,45 @@ class PinnedArray:
             pass
 
 
+class Comm:
+    """Owns one `dabry_comm*`: the library's own communicator over the GPUs of a job (NCCL inside libdabry_b200.so).
+    `Comm.unique_id()` on rank 0, ship the bytes to the other ranks, then `Comm(device, rank, world, id)` everywhere
+    (collective)."""
+
+    @staticmethod
+    def unique_id():
+        lib = library()
+        buf = C.create_string_buffer(COMM_ID_BYTES)
+        rc = lib.dabry_comm_unique_id(buf)
+        if rc != 0:
+            raise NativeError(rc, (lib.dabry_comm_last_error() or b'dabry_comm_unique_id failed').decode())
+        return buf.raw
+
+    def __init__(self, device, rank, world, unique_id):
+        self._lib = library()
+        self._c = C.c_void_p()
+        self.rank, self.world, self.device = rank, world, device
+        buf = C.create_string_buffer(bytes(unique_id), COMM_ID_BYTES)
+        rc = self._lib.dabry_comm_create(device, rank, world, buf, C.byref(self._c))
+        if rc != 0:
+            raise NativeError(rc, (self._lib.dabry_comm_last_error() or b'dabry_comm_create failed').decode())
+
+    @property
+    def pointer(self):
+        return self._c
+
+    def close(self):
+        if getattr(self, '_c', None):
+            self._lib.dabry_comm_destroy(self._c)
+            self._c = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Handle:
     """Owns one `dabry_solver*`."""
 
@@ -310,6 +360,15 @@ class Handle:
         cost = C.c_double()
         self.call('dabry_get_solution', C.byref(site), C.byref(cost))
         return site.value, cost.value
+
+    def attach_comm(self, comm):
+        self.call('dabry_attach_comm', comm.pointer if comm is not None else None)
+        self._keep = tuple(self._keep) + (comm,)
+
+    def global_solution(self):
+        cost, owner, steps = C.c_double(), C.c_int32(), C.c_uint64()
+        self.call('dabry_get_global_solution', C.byref(cost), C.byref(owner), C.byref(steps))
+        return cost.value, owner.value, steps.value
 
     def stats(self):
         s = Stats()

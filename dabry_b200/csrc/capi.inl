@@ -11,11 +11,19 @@ struct dabry_solver {
 
 static thread_local std::string g_create_error;
 
-// every entry point first makes the handle's device current: a process may hold handles on several GPUs
+struct dabry_comm {
+    DABRY_BACKEND::Comm* comm;
+};
+
+static thread_local std::string g_comm_error;
+
+// every entry point first takes the call guard of the handle's backend: it makes the handle's device current (a process
+// may hold handles on several GPUs) and serialises the calls of all handles on that device, which share the constant
+// memory the problem description lives in (CudaBackend::CallGuard)
 #define DABRY_GUARD(h)                 \
     if (!(h) || !(h)->eng) return DABRY_ERR_INVALID; \
     dabry::Engine<DABRY_BACKEND>& E = *(h)->eng;     \
-    E.be.activate()
+    DABRY_BACKEND::CallGuard call_guard_(E.be)
 
 extern "C" {
 
@@ -57,6 +65,11 @@ int dabry_create(const dabry_config* c, dabry_solver** out) {
     // DABRY_B200_DEBUG_TIMING=1: host wall time of the two halves of dabry_create on stderr (diagnostic)
     const bool timing = getenv("DABRY_B200_DEBUG_TIMING") != nullptr;
     const auto t0 = std::chrono::steady_clock::now();
+    // dyadic site indices are root * 2^max_depth (solver_ef.py:197-202) in int64
+    if (c->max_depth >= 62 || c->n_roots > (((int64_t) 1 << 62) >> c->max_depth)) {
+        g_create_error = "dabry_config: n_roots * 2^max_depth does not fit the 64-bit dyadic site index";
+        return DABRY_ERR_INVALID;
+    }
     dabry::Engine<DABRY_BACKEND>* e = new dabry::Engine<DABRY_BACKEND>(*c);
     if (!e->be.open(c->device)) {
         g_create_error = e->be.error();
@@ -80,8 +93,7 @@ int dabry_create(const dabry_config* c, dabry_solver** out) {
 
 void dabry_destroy(dabry_solver* h) {
     if (!h) return;
-    if (h->eng) h->eng->be.activate();
-    delete h->eng;
+    if (h->eng) DABRY_BACKEND::destroy_locked(h->eng->be, [&] { delete h->eng; });
     delete h;
 }
 
@@ -95,6 +107,13 @@ int dabry_set_flow_grid(dabry_solver* h, const double* values, const double* gra
     DABRY_GUARD(h);
     if (!lo || !hi) return E.fail(DABRY_ERR_INVALID, "flow grid: bounds missing");
     return E.set_flow_grid(values, grad, nt, nx, ny, unsteady, lo, hi, w);
+}
+
+int dabry_set_flow_grid_shared(dabry_solver* h, const double* values, int32_t nt, int32_t nx, int32_t ny, int32_t unsteady,
+                               const double lo[3], const double hi[3], const dabry_wrapper* w) {
+    DABRY_GUARD(h);
+    if (!lo || !hi) return E.fail(DABRY_ERR_INVALID, "flow grid: bounds missing");
+    return E.set_flow_grid(values, nullptr, nt, nx, ny, unsteady, lo, hi, w, true);
 }
 
 int dabry_set_flow_program(dabry_solver* h, const dabry_leaf* leaves, int32_t n, const double* tables, int64_t n_tab,
@@ -273,6 +292,48 @@ int dabry_set_cost_map_device(dabry_solver* h, const double* d_map) {
     DABRY_GUARD(h);
     if (!d_map) return DABRY_ERR_INVALID;
     return E.set_cost_map(d_map, true);
+}
+
+// ---- in-library collectives ----
+int dabry_comm_unique_id(void* id) {
+    if (!id) return DABRY_ERR_INVALID;
+    return DABRY_BACKEND::comm_unique_id(id, g_comm_error) ? DABRY_OK : DABRY_ERR_UNSUPPORTED;
+}
+
+int dabry_comm_create(int32_t device, int32_t rank, int32_t world, const void* id, dabry_comm** out) {
+    if (!out || !id || world < 1 || rank < 0 || rank >= world) return DABRY_ERR_INVALID;
+    *out = nullptr;
+    DABRY_BACKEND::Comm* c = DABRY_BACKEND::comm_create(device, rank, world, id, g_comm_error);
+    if (!c) return DABRY_ERR_UNSUPPORTED;
+    *out = new dabry_comm{c};
+    return DABRY_OK;
+}
+
+void dabry_comm_destroy(dabry_comm* c) {
+    if (!c) return;
+    DABRY_BACKEND::comm_destroy(c->comm);
+    delete c;
+}
+
+const char* dabry_comm_last_error(void) { return g_comm_error.c_str(); }
+
+int dabry_attach_comm(dabry_solver* h, dabry_comm* c) {
+    DABRY_GUARD(h);
+    E.comm = c ? c->comm : nullptr;
+    return DABRY_OK;
+}
+
+int dabry_solve_sharded(dabry_solver* h, int32_t variant, const double* costates) {
+    DABRY_GUARD(h);
+    return E.solve_sharded(variant, costates);
+}
+
+int dabry_get_global_solution(dabry_solver* h, double* cost, int32_t* owner_rank, uint64_t* total_rk_steps) {
+    DABRY_GUARD(h);
+    if (cost) *cost = E.global_cost;
+    if (owner_rank) *owner_rank = E.global_owner;
+    if (total_rk_steps) *total_rk_steps = E.global_rk_steps;
+    return DABRY_OK;
 }
 
 int dabry_eval_rhs(dabry_solver* h, int64_t n, const double* t, const double* y, double* dy) {

@@ -10,6 +10,7 @@
 #include <unordered_map>
 
 #include "engine.cuh"
+#include "nccl_dyn.cuh"
 
 namespace dabry {
 
@@ -221,6 +222,10 @@ public:
                     if (e) cudaEventDestroy(e);
                 cudaStreamDestroy(copy_stream_);
             }
+            for (auto& sp : spans_) {
+                cudaEventDestroy(sp.first);
+                cudaEventDestroy(sp.second);
+            }
             if (d_small_) cudaFreeAsync(d_small_, stream_);
             if (d_block_sum_) cudaFreeAsync(d_block_sum_, stream_);
             cudaStreamSynchronize(stream_);
@@ -417,6 +422,160 @@ public:
         chk(cudaMemcpyToSymbolAsync(c_problem, &P, sizeof(ProblemDev), 0, cudaMemcpyHostToDevice, stream_), "bind problem");
     }
 
+    void upload_async(void* d, const void* h, size_t bytes) {
+        chk(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, stream_), "H2D copy");
+    }
+
+    // ---- process-wide state of one device: the problem description of every handle goes through ONE __constant__
+    // symbol (model.cuh), so the entry points of all handles on a device are serialised (CallGuard, taken by every
+    // C entry point), and a handle that binds its problem first makes its stream wait for the kernels of the handle
+    // that used the constants before it.  Handles on different devices run concurrently.
+    struct DeviceState {
+        std::mutex mutex;
+        cudaEvent_t last_use = nullptr;
+        const void* last_owner = nullptr;
+    };
+    static DeviceState& device_state(int device) {
+        static std::mutex table_mutex;
+        static std::map<int, DeviceState> table;
+        std::lock_guard<std::mutex> lock(table_mutex);
+        return table[device];
+    }
+    class CallGuard {
+    public:
+        explicit CallGuard(CudaBackend& be) : be_(be), st_(device_state(be.device_)) {
+            st_.mutex.lock();
+            be_.activate();
+            if (be_.stream_ && st_.last_owner && st_.last_owner != &be_ && st_.last_use)
+                cudaStreamWaitEvent(be_.stream_, st_.last_use, 0);
+        }
+        ~CallGuard() {
+            if (be_.stream_) {
+                if (!st_.last_use) cudaEventCreateWithFlags(&st_.last_use, cudaEventDisableTiming);
+                if (st_.last_use) cudaEventRecord(st_.last_use, be_.stream_);
+                st_.last_owner = &be_;
+            }
+            st_.mutex.unlock();
+        }
+        CallGuard(const CallGuard&) = delete;
+        CallGuard& operator=(const CallGuard&) = delete;
+
+    private:
+        CudaBackend& be_;
+        DeviceState& st_;
+    };
+
+    template <class Fn>
+    static void destroy_locked(CudaBackend& be, Fn&& destroy) {  // dabry_destroy: the backend dies inside the lock
+        DeviceState& st = device_state(be.device_);
+        std::lock_guard<std::mutex> lock(st.mutex);
+        be.activate();
+        if (st.last_owner == &be) st.last_owner = nullptr;  // ~CudaBackend drains its stream
+        destroy();
+    }
+
+    // ---- collectives: NCCL on the solver's stream (nccl_dyn.cuh) ---------------------------------------------------
+    struct Comm {
+        nccl::Comm_t comm = nullptr;
+        int rank = 0, world = 1, device = 0;
+    };
+    static int comm_rank(const Comm* c) { return c->rank; }
+    static int comm_world(const Comm* c) { return c->world; }
+    static bool comm_unique_id(void* id, std::string& err) {
+        const nccl::Api& n = nccl::api();
+        if (!n.ok()) {
+            err = n.error;
+            return false;
+        }
+        nccl::UniqueId uid;
+        const int rc = n.GetUniqueId(&uid);
+        if (rc != 0) {
+            err = std::string("ncclGetUniqueId: ") + n.GetErrorString(rc);
+            return false;
+        }
+        memcpy(id, &uid, sizeof(uid));
+        return true;
+    }
+    static Comm* comm_create(int device, int rank, int world, const void* id, std::string& err) {
+        const nccl::Api& n = nccl::api();
+        if (!n.ok()) {
+            err = n.error;
+            return nullptr;
+        }
+        if (cudaSetDevice(device) != cudaSuccess) {
+            cudaGetLastError();
+            err = "dabry_comm_create: bad device";
+            return nullptr;
+        }
+        nccl::UniqueId uid;
+        memcpy(&uid, id, sizeof(uid));
+        Comm* c = new Comm;
+        c->rank = rank;
+        c->world = world;
+        c->device = device;
+        const int rc = n.CommInitRank(&c->comm, world, uid, rank);
+        if (rc != 0) {
+            err = std::string("ncclCommInitRank: ") + n.GetErrorString(rc);
+            delete c;
+            return nullptr;
+        }
+        return c;
+    }
+    static void comm_destroy(Comm* c) {
+        if (!c) return;
+        if (c->comm) {
+            cudaSetDevice(c->device);
+            nccl::api().CommDestroy(c->comm);
+        }
+        delete c;
+    }
+    bool nccl_ok(int rc, const char* what) {
+        if (rc == 0) return true;
+        if (err_.empty()) err_ = std::string(what) + ": " + nccl::api().GetErrorString(rc);
+        return false;
+    }
+    // ring: n doubles to rank - 1, n doubles from rank + 1, one group (ncclGroupStart / End) so that neither blocks
+    void comm_ring_shift(Comm* c, const double* send, double* recv, int64_t n) {
+        const nccl::Api& a = nccl::api();
+        const int to = (c->rank + c->world - 1) % c->world, from = (c->rank + 1) % c->world;
+        nccl_ok(a.GroupStart(), "ncclGroupStart");
+        nccl_ok(a.Send(send, (size_t) n, nccl::kFloat64, to, c->comm, stream_), "ncclSend");
+        nccl_ok(a.Recv(recv, (size_t) n, nccl::kFloat64, from, c->comm, stream_), "ncclRecv");
+        nccl_ok(a.GroupEnd(), "ncclGroupEnd");
+    }
+    void comm_allreduce_min_f64(Comm* c, double* buf, int64_t n) {
+        nccl_ok(nccl::api().AllReduce(buf, buf, (size_t) n, nccl::kFloat64, nccl::kMin, c->comm, stream_), "ncclAllReduce");
+    }
+    // recv holds world x bytes; in place when send == recv + rank * bytes
+    void comm_allgather(Comm* c, const void* send, void* recv, size_t bytes) {
+        nccl_ok(nccl::api().AllGather(send, recv, bytes, nccl::kUint8, c->comm, stream_), "ncclAllGather");
+    }
+
+    // device time of stretches that must not wait for the device (the collectives): event pairs, read at span_collect
+    void span_begin() {
+        if (span_used_ == spans_.size()) {
+            cudaEvent_t a = nullptr, b = nullptr;
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            spans_.push_back({a, b});
+        }
+        cudaEventRecord(spans_[span_used_].first, stream_);
+    }
+    void span_end() { cudaEventRecord(spans_[span_used_++].second, stream_); }
+    double span_collect() {
+        double total = 0.;
+        for (size_t i = 0; i < span_used_; ++i) {
+            float ms = 0.f;
+            if (cudaEventSynchronize(spans_[i].second) == cudaSuccess &&
+                cudaEventElapsedTime(&ms, spans_[i].first, spans_[i].second) == cudaSuccess)
+                total += ms;
+            else
+                cudaGetLastError();
+        }
+        span_used_ = 0;
+        return total;
+    }
+
     template <class F>
     void launch(int64_t n, const F& f) {
         if (n <= 0 || !ok()) return;
@@ -506,6 +665,8 @@ private:
     void* d_small_ = nullptr;
     int32_t* d_block_sum_ = nullptr;
     int64_t block_sum_cap_ = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans_;
+    size_t span_used_ = 0;
     uint64_t launches_ = 0;
     std::string err_;
 };

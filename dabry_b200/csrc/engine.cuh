@@ -38,8 +38,11 @@ static_assert(sizeof(PenaltyDesc) == sizeof(dabry_penalty), "penalty layout");
 static_assert(DABRY_MAX_TARGET_EVENTS == 4, "abi");
 
 struct Counters {  // device-resident
-    unsigned long long rk_steps, ivp_calls, spare0, spare1;
+    unsigned long long rk_steps, ivp_calls, rk_steps_free, spare1;  // rk_steps_free: the free-arc kernel's share
 };
+
+DABRY_HD int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }
+DABRY_HD int64_t imax64(int64_t a, int64_t b) { return a > b ? a : b; }
 
 DABRY_HD void counter_add(unsigned long long* c, unsigned long long v) {
 #if defined(__CUDA_ARCH__)
@@ -167,6 +170,7 @@ struct FreeArcPhase {  // the hot kernel: one thread per extremal, free arc with
         site_free_arc<FK, METHOD, CHUNKED>(problem(), S, s, index_t, attempts, calls, budget, t_park, resume_only != 0);
         DABRY_TRACE_FREE_ARC(s, attempts);
         counter_add(&counters->rk_steps, attempts);
+        counter_add(&counters->rk_steps_free, attempts);
         counter_add(&counters->ivp_calls, calls);
         if (CHUNKED) running[i] = (S.flags[s] & SITE_RUNNING) ? 0 : -1;
     }
@@ -512,11 +516,15 @@ struct BoundaryPhase {  // one work item per (packet, time index)
     int32_t do_import, n_time;
     int64_t root_count, block, packet;  // export: first root of local block k; import: ghost slot root_count + k
     double* all;
+    // import: ghost k is packet (k + shift) % n_packets of the buffer.  The in-library ring exchange receives the next
+    // rank's packets in that rank's block order: block k of rank r is followed by block k of rank r + 1, except on the
+    // last rank, where it is followed by block k + 1 of rank 0 (shift 1)
+    int64_t shift = 0, n_packets = 1;
     DABRY_HD void operator()(int64_t i) const {
         const int64_t pk = i / n_time;
         const int k = (int) (i % n_time);
         const int site = (int) (do_import ? root_count + pk : pk * block);
-        double* buf = all + pk * packet;
+        double* buf = all + (do_import ? (pk + shift) % n_packets : pk) * packet;
         const int64_t o = S.at(site, k);
         double* row = buf + DABRY_BOUNDARY_HEADER + 7 * k;
         if (!do_import) {
@@ -526,7 +534,9 @@ struct BoundaryPhase {  // one work item per (packet, time index)
                 buf[0] = (double) S.index_t_init[site]; buf[1] = (double) S.n_samples[site];
                 buf[2] = (double) S.closure[site]; buf[3] = (double) S.obstacle[site];
                 buf[4] = (double) S.index_t_obs[site]; buf[5] = (double) S.trigo[site];
-                buf[6] = (double) S.depth[site]; buf[7] = S.cost0[site]; buf[8] = (double) S.dyadic[site];
+                buf[6] = (double) S.depth[site]; buf[7] = S.cost0[site];
+                const int64_t dy = S.dyadic[site];  // raw bits: a dyadic index may exceed 2^53
+                memcpy(&buf[8], &dy, sizeof(dy));
             }
         } else {
             S.xp[o] = Sample{row[0], row[1], row[2], row[3]};
@@ -537,7 +547,10 @@ struct BoundaryPhase {  // one work item per (packet, time index)
                 S.index_t_init[site] = (int) buf[0]; S.n_samples[site] = (int) buf[1];
                 S.closure[site] = (int) buf[2]; S.obstacle[site] = (int) buf[3];
                 S.index_t_obs[site] = (int) buf[4]; S.trigo[site] = (int) buf[5];
-                S.depth[site] = (int) buf[6]; S.cost0[site] = buf[7]; S.dyadic[site] = (int64_t) buf[8];
+                S.depth[site] = (int) buf[6]; S.cost0[site] = buf[7];
+                int64_t dy;
+                memcpy(&dy, &buf[8], sizeof(dy));
+                S.dyadic[site] = dy;
                 S.flags[site] = SITE_GHOST;
                 S.check_next[site] = 0;
             }
@@ -612,6 +625,8 @@ public:
         be.free(d_arr_index);
         be.free(d_arr_cost);
         be.free(d_counters);
+        be.free(d_send);
+        be.free(d_recv);
         be.free(d_scratch);
     }
 
@@ -626,8 +641,10 @@ public:
     }
 
     // ---- problem ----
+    // shared: every rank of the attached communicator holds the same `values`; each uploads 1 / world of them and the
+    // rest arrives from the peers over NVLink (all-gather in place) instead of world x the same bytes over PCIe
     int set_flow_grid(const double* values, const double* grad, int nt, int nx, int ny, int unsteady,
-                      const double* lo, const double* hi, const dabry_wrapper* w) {
+                      const double* lo, const double* hi, const dabry_wrapper* w, bool shared = false) {
         if (!values || nt < 1 || nx < 3 || ny < 3 || (!unsteady && nt != 1))
             return fail(DABRY_ERR_INVALID, "flow grid: need values, nt >= 1, nx >= 3, ny >= 3 (nt == 1 if steady)");
         drop_pending_grid();
@@ -635,7 +652,10 @@ public:
         const int64_t nodes = (int64_t) nt * nx * ny;
         const int64_t records = (int64_t) (nt + 1) * nx * ny;
         if (records >= (int64_t) 1 << 31) return fail(DABRY_ERR_CAPACITY, "flow grid: more than 2^31 records");
-        double* d_values = (double*) be.alloc(sizeof(double) * 2 * nodes);
+        const int world = shared ? comm_world() : 1;
+        // all-gather needs equal shares: the staging buffer is padded to world x share doubles
+        const int64_t share = (2 * nodes + world - 1) / world;
+        double* d_values = (double*) be.alloc(sizeof(double) * (world > 1 ? share * world : 2 * nodes));
         double* d_grad = grad ? (double*) be.alloc(sizeof(double) * 4 * nodes) : nullptr;
         be.free(d_grid);
         d_grid = (double*) be.alloc((cfg.dtype == DABRY_F32 ? sizeof(float) : sizeof(double)) * 12 * records);
@@ -646,9 +666,18 @@ public:
         // alive and unchanged until that solve (or any other call that needs the whole grid) returns.
         // (only grids whose copy takes longer than the extra launches of the windows cost: 64 MB is 1.3 ms of PCIe)
         const bool big = stream_upload > 1 || sizeof(double) * 2 * (size_t) nodes >= ((size_t) 64 << 20);
-        const bool streamed = stream_upload && big && unsteady && !grad && nt >= 2 * kGridGroups &&
+        const bool streamed = world == 1 && stream_upload && big && unsteady && !grad && nt >= 2 * kGridGroups &&
                               (!w || w->scale_time > 0.) && be.host_is_pinned(values);
-        if (!streamed) be.upload(d_values, values, sizeof(double) * 2 * nodes);
+        if (world > 1) {
+            const int64_t first = share * comm_rank();
+            const int64_t mine = imax64(0, imin64(share, 2 * nodes - first));
+            if (mine > 0) be.upload_async(d_values + first, values + first, sizeof(double) * mine);
+            be.span_begin();
+            be.comm_allgather(comm, d_values + first, d_values, sizeof(double) * share);
+            be.span_end();
+        } else if (!streamed) {
+            be.upload(d_values, values, sizeof(double) * 2 * nodes);
+        }
         if (grad) be.upload(d_grad, grad, sizeof(double) * 4 * nodes);
         GridDesc& G = P.field.grid;
         G.data = d_grid;
@@ -851,6 +880,8 @@ public:
         be.zero(d_counters, sizeof(Counters));
         stats.rounds = 0;
         stats.ms_integrate = stats.ms_obstacle = stats.ms_resample = stats.ms_trim = stats.ms_arrival = stats.ms_total = 0.;
+        stats.ms_comm = 0.;
+        be.span_collect();
         return check();
     }
 
@@ -1109,8 +1140,10 @@ public:
         be.download(&c, d_counters, sizeof(c));
         stats.rk_steps = c.rk_steps;
         stats.ivp_calls = c.ivp_calls;
+        stats.rk_steps_free = c.rk_steps_free;
         stats.rhs_evals = cfg.integrator == DABRY_RK4_FIXED ? 4 * c.rk_steps + c.ivp_calls : 6 * c.rk_steps + 2 * c.ivp_calls;
         stats.kernel_launches = be.launches();
+        stats.ms_comm += be.span_collect();
         stats.n_sites = n_sites;  // device slots, including the ghost slot of a sharded ring (record flag bit 0)
         stats.capacity = S.capacity;
         *out = stats;
@@ -1144,11 +1177,113 @@ public:
         double* d = on_device ? const_cast<double*>(packed) : (double*) scratch(sizeof(double) * n);
         if (!d) return fail(DABRY_ERR_CAPACITY, "out of device memory");
         if (!on_device) be.upload(d, packed, sizeof(double) * n);
-        BoundaryPhase ph{S, 1, cfg.n_time, cfg.root_count, shard_b, boundary_doubles(), d};
+        BoundaryPhase ph{S, 1, cfg.n_time, cfg.root_count, shard_b, boundary_doubles(), d, 0, n_blocks};
         be.launch(n_blocks * cfg.n_time, ph);
         if (on_device) be.sync();
         return check();
     }
+
+    // ---- in-library collectives: everything below is enqueued on the solver's stream, no host round trip
+    typedef typename B::Comm Comm;
+    Comm* comm = nullptr;  // not owned (dabry_attach_comm)
+    int comm_world() const { return comm ? B::comm_world(comm) : 1; }
+    int comm_rank() const { return comm ? B::comm_rank(comm) : 0; }
+
+    // ring boundary: the first root of every local block -> the previous rank, whose ghosts they become
+    int exchange_boundary() {
+        if (comm_world() <= 1) return DABRY_OK;
+        if (!has_ghost) return fail(DABRY_ERR_INVALID, "sharded solve: this handle owns the whole ring");
+        const int64_t n = boundary_doubles() * n_blocks;
+        if (n > xchg_doubles) {
+            be.free(d_send);
+            be.free(d_recv);
+            d_send = (double*) be.alloc(sizeof(double) * n);
+            d_recv = (double*) be.alloc(sizeof(double) * n);
+            if (!d_send || !d_recv) return fail(DABRY_ERR_CAPACITY, "out of device memory (boundary buffers)");
+            xchg_doubles = n;
+        }
+        be.span_begin();  // timed by events that are read at dabry_get_stats: nothing here waits for the device
+        BoundaryPhase ex{S, 0, cfg.n_time, cfg.root_count, shard_b, boundary_doubles(), d_send, 0, n_blocks};
+        be.launch(n_blocks * cfg.n_time, ex);
+        be.comm_ring_shift(comm, d_send, d_recv, n);
+        const int64_t shift = comm_rank() == comm_world() - 1 ? 1 : 0;
+        BoundaryPhase im{S, 1, cfg.n_time, cfg.root_count, shard_b, boundary_doubles(), d_recv, shift, n_blocks};
+        be.launch(n_blocks * cfg.n_time, im);
+        be.span_end();
+        return check();
+    }
+
+    // SolverEFResampling.solve / SolverEFTrimming.solve over all ranks of the attached communicator: the ring of roots
+    // is sharded by theta_0 (config.root_offset / root_count / shard_block), the ring boundary travels after the roots
+    // are integrated (Trimming: every sub-frame), the trimming cost map is all-reduced (min) in place, and the arrival
+    // records of all ranks are gathered at the end (global_cost / global_owner / global_rk_steps).
+    int solve_sharded(int variant_, const double* costates) {
+        be.tic_total();
+        if (int rc = setup(variant_, costates)) return rc;
+        const bool multi = comm_world() > 1;
+        if (multi && !has_ghost) return fail(DABRY_ERR_INVALID, "sharded solve: config.root_count must be a shard of n_roots");
+        if (variant == DABRY_TRIMMING) {
+            const int n = n_subframes();
+            for (int i = 0; i < n; ++i) {
+                if (int rc = step_trim_integrate()) return rc;
+                if (multi)
+                    if (int rc = exchange_boundary()) return rc;
+                if (int rc = step_trim_refine()) return rc;
+                if (multi) {
+                    be.span_begin();
+                    be.comm_allreduce_min_f64(comm, d_map, (int64_t) C.cm_nx * C.cm_ny);
+                    be.span_end();
+                }
+                if (int rc = step_trim_close()) return rc;
+            }
+        } else {
+            const int n = variant == DABRY_SIMPLE ? 1 : cfg.max_depth;
+            for (int i = 0; i < n; ++i) {
+                if (int rc = step_integrate()) return rc;
+                if (multi && i == 0)
+                    if (int rc = exchange_boundary()) return rc;
+                if (int rc = step_resample()) return rc;
+                // every rank runs the same number of rounds only where a collective follows; after round 0 none does,
+                // so a rank whose round neither integrated nor created a site can stop on its own (see solve())
+                if (shoot_end == shoot_begin) break;
+            }
+        }
+        if (int rc = finish()) return rc;
+        // arrival-time argmin over ranks (check_solutions, solver_ef.py:667-685) + the totals of the throughput metric
+        Counters c;
+        be.download(&c, d_counters, sizeof(c));
+        const int world = comm_world(), rank = comm_rank();
+        std::vector<double> all(4 * (size_t) world, 0.);
+        double mine[4] = {solution_cost == solution_cost ? solution_cost : INFINITY, (double) c.rk_steps, (double) n_sites, 0.};
+        if (multi) {
+            double* d = (double*) scratch(sizeof(double) * 4 * (world + 1));
+            if (!d) return fail(DABRY_ERR_CAPACITY, "out of device memory");
+            be.upload(d + 4 * world, mine, sizeof(mine));
+            be.span_begin();
+            be.comm_allgather(comm, d + 4 * world, d, sizeof(mine));
+            be.span_end();
+            be.download(all.data(), d, sizeof(double) * 4 * world);
+        } else {
+            memcpy(all.data(), mine, sizeof(mine));
+        }
+        global_cost = INFINITY;
+        global_owner = -1;
+        global_rk_steps = 0;
+        for (int r = 0; r < world; ++r) {
+            if (all[4 * r] < global_cost) {  // ties: lowest rank
+                global_cost = all[4 * r];
+                global_owner = r;
+            }
+            global_rk_steps += (uint64_t) all[4 * r + 1];
+        }
+        if (!(global_cost < INFINITY)) global_cost = NAN;
+        (void) rank;
+        stats.ms_total = be.toc_total();
+        return check();
+    }
+    double global_cost = NAN;
+    int32_t global_owner = -1;
+    uint64_t global_rk_steps = 0;
 
     // ---- evaluation hooks ----
     int eval_rhs(int64_t n, const double* t, const double* y, double* dy) {
@@ -1202,6 +1337,9 @@ private:
     int32_t* d_arr_index = nullptr;
     double* d_arr_cost = nullptr;
     Counters* d_counters = nullptr;
+    double* d_send = nullptr;   // ring-boundary packets of the in-library exchange
+    double* d_recv = nullptr;
+    int64_t xchg_doubles = 0;
     void* d_scratch = nullptr;
     size_t scratch_bytes = 0;
     int64_t aux_capacity = 0;

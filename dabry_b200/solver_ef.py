@@ -278,7 +278,7 @@ class SolverEF(ABC):
                  target_radius: Optional[float] = None, abs_max_step: Optional[float] = None,
                  rel_max_step: Optional[float] = 0.01, *, device: int = 0, max_sites: int = 0,
                  root_range: Optional[tuple] = None, shard: Optional[tuple] = None, integrator: str = 'dopri5',
-                 dtype: str = 'f64'):
+                 dtype: str = 'f64', comm=None):
         if mode not in self._ALL_MODES:
             raise ValueError('Mode %s is not defined' % mode)
         if mode == 'energy':
@@ -336,6 +336,9 @@ class SolverEF(ABC):
             if n_costate_sectors % (world * block) != 0:
                 raise ValueError('n_costate_sectors must be a multiple of world * block')
             self.root_range = (rank * block, n_costate_sectors // world)
+        # comm: the library's communicator over the GPUs of a sharded job (dabry_b200.distributed.library_comm); with it
+        # solve() runs dabry_solve_sharded and the flow grid is uploaded cooperatively (1 / world per rank + all-gather)
+        self._comm = comm
         self._event_names = list(self.events.keys())
         self._handle: Optional[nat.Handle] = None
         self._stale = True
@@ -425,7 +428,9 @@ class SolverEF(ABC):
 
     def _make_handle(self, cfg):
         handle = nat.Handle(cfg)
-        low.apply_flow(handle, self.pb.model.ff)
+        if self._comm is not None:
+            handle.attach_comm(self._comm)
+        low.apply_flow(handle, self.pb.model.ff, shared=self._comm is not None)
         low.apply_obstacles(handle, self.pb.obstacles)
         low.apply_penalty(handle, self.pb.penalty)
         return handle
@@ -585,12 +590,16 @@ class SolverEFResampling(SolverEF):
     def solve(self):
         handle = self._ensure_handle()
         costates = self._root_costates()
-        handle.call('dabry_solve', self._VARIANT, nat.dptr(costates))
+        handle.call('dabry_solve_sharded' if self._comm is not None else 'dabry_solve', self._VARIANT,
+                    nat.dptr(costates))
         self._invalidate()
-        self.depth = self.max_depth
+        self._after_solve()
         self.check_solutions(_finished=True)
         if self.solution_site is not None:
             self.extrapolate_back_traj(self.solution_site)  # the other solution sites: on first access of traj_full
+
+    def _after_solve(self):
+        self.depth = self.max_depth
 
     def check_solutions(self, _finished=False):
         """Sites with a grid sample strictly inside the target disc; the cheapest is `solution_site`, those within
@@ -810,8 +819,7 @@ class SolverEFTrimming(SolverEFResampling):
         self._invalidate()
         self.i_subframe += 1
 
-    def solve(self):
-        super().solve()
+    def _after_solve(self):
         self.i_subframe = self.n_subframes
 
     @property

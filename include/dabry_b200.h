@@ -4,8 +4,10 @@
  * interface `SolverEF*.setup()/step()/solve()` (dabry/solver_ef.py:281-857).  Each entry point below names the
  * reference code it replaces.  Conventions: plain C, every pointer is a HOST pointer owned by the caller unless
  * stated, every function returns 0 on success and a negative dabry_status on error, `dabry_last_error` gives the
- * message.  A handle is bound to one CUDA device and one stream and is not thread-safe.  There is no host execution
- * path: dabry_create fails with DABRY_ERR_NO_DEVICE when no CUDA device is usable.
+ * message.  A handle is bound to one CUDA device and one stream and is not thread-safe.  Different handles may be
+ * driven from different host threads: the calls of all handles on ONE device are serialised inside the library (they
+ * share the constant memory the problem description lives in), handles on different devices run concurrently.  There
+ * is no host execution path: dabry_create fails with DABRY_ERR_NO_DEVICE when no CUDA device is usable.
  */
 #ifndef DABRY_B200_H
 #define DABRY_B200_H
@@ -17,12 +19,14 @@
 extern "C" {
 #endif
 
-#define DABRY_ABI_VERSION 1
+#define DABRY_ABI_VERSION 2
 #define DABRY_MAX_OBSTACLES 8
 #define DABRY_MAX_LEAVES 8
 #define DABRY_MAX_TARGET_EVENTS 4
 
 typedef struct dabry_solver dabry_solver;
+typedef struct dabry_comm dabry_comm; /* a communicator over the GPUs of one job (NCCL), see "in-library collectives" */
+#define DABRY_COMM_ID_BYTES 128
 
 enum dabry_status {
     DABRY_OK = 0,
@@ -154,6 +158,8 @@ typedef struct dabry_stats {
     double ms_integrate, ms_resample, ms_trim, ms_arrival, ms_total;   /* device time by phase (CUDA events); ms_integrate = free-arc kernel */
     double ms_upload;        /* flow grid repack + derivative kernels */
     double ms_obstacle;      /* obstacle entry + boundary-following kernel (captured extremals only) */
+    double ms_comm;          /* in-library collectives of dabry_solve_sharded (events on the solver's stream) */
+    uint64_t rk_steps_free;  /* the share of rk_steps taken inside the free-arc kernel (what ms_integrate times) */
 } dabry_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------ */
@@ -263,6 +269,35 @@ int dabry_export_boundary_device(dabry_solver* h, double* d_packed);
 int dabry_import_boundary_device(dabry_solver* h, const double* d_packed);
 int dabry_get_cost_map_device(dabry_solver* h, int32_t full, double* d_out);
 int dabry_set_cost_map_device(dabry_solver* h, const double* d_map);
+
+/* ---- in-library collectives ------------------------------------------------------------------ */
+/* One process per GPU.  The ring of roots is sharded by theta_0 through dabry_config (root_offset / root_count /
+ * shard_block / shard_world), the flow grid is replicated, and the library itself carries the three exchanges of the
+ * reference's loops over NCCL, enqueued on the solver's stream with no host round trip:
+ *   - ring boundary (solver_ef.py:468-469): ncclSend / ncclRecv of one packet per local block inside one
+ *     ncclGroupStart / ncclGroupEnd, after the roots are integrated (Trimming: every sub-frame);
+ *   - trimming cost map (solver_ef.py:825-828): ncclAllReduce(ncclMin) in place on the device map, every sub-frame;
+ *   - check_solutions (solver_ef.py:667-685): ncclAllGather of (arrival cost, step count) per rank at the end.
+ * NCCL is bound at run time (the process's own copy - e.g. PyTorch's - else libnccl.so.2); without it
+ * dabry_comm_unique_id / dabry_comm_create return DABRY_ERR_UNSUPPORTED and dabry_comm_last_error says why.
+ * Rank 0 calls dabry_comm_unique_id and hands the DABRY_COMM_ID_BYTES to the other ranks by any means (the Python
+ * host mirror broadcasts them through torch.distributed); every rank then calls dabry_comm_create, which is collective.
+ * A communicator outlives the solvers attached to it (one solver per solve() is the reference's pattern). */
+int dabry_comm_unique_id(void* id);
+int dabry_comm_create(int32_t device, int32_t rank, int32_t world, const void* id, dabry_comm** out);
+void dabry_comm_destroy(dabry_comm* comm);
+const char* dabry_comm_last_error(void);
+int dabry_attach_comm(dabry_solver* h, dabry_comm* comm); /* NULL detaches; the handle does not own it */
+/* dabry_set_flow_grid for ranks that all hold the same `values` (grad is computed on the device): each rank uploads
+ * 1 / world of the samples over PCIe and the rest arrives from its peers over NVLink (ncclAllGather in place).
+ * Collective over the attached communicator; without one it is dabry_set_flow_grid. */
+int dabry_set_flow_grid_shared(dabry_solver* h, const double* values, int32_t nt, int32_t nx, int32_t ny,
+                               int32_t unsteady, const double lo[3], const double hi[3], const dabry_wrapper* wrapper);
+/* dabry_solve over all ranks of the attached communicator (collective); without one it is dabry_solve. */
+int dabry_solve_sharded(dabry_solver* h, int32_t variant, const double* costates);
+/* Global optimum after dabry_solve_sharded: arrival cost (NaN: none), the rank that holds the optimal extremal (lowest
+ * rank among equals, -1: none) and the RK step attempts of all ranks. */
+int dabry_get_global_solution(dabry_solver* h, double* cost, int32_t* owner_rank, uint64_t* total_rk_steps);
 
 /* ---- evaluation hooks used by the parity tests ---------------------------------------------------------- */
 /* SolverEF.dyn_augsys(t, y) (solver_ef.py:355-359) for n points: t [n], y [n][4] -> dy [n][4]. */

@@ -96,3 +96,33 @@ def solver_record(solver, full: bool = False, next_nb: bool = False) -> dict:
                     nb[i, k] = ids[id(o)]
         rec['next_nb'] = nb
     return rec
+
+
+EXACT_SITE_FIELDS = ['index_t_init', 'traj_len', 'closure', 'neuter', 'obstacle', 'index_t_obs', 'obs_trigo',
+                     'index_t_check_next']
+FLOAT_SITE_FIELDS = ['first', 'last', 'state_sum', 't_enter_obs']
+
+
+def differing_sites(rec, g, tol=1e-9):
+    """Names of the sites whose record differs between two flattened runs, or that exist in only one of them.
+    Integer fields and flags must be equal; floating-point fields may differ by tol * max(1, |reference value|) per
+    element (costates reach 1e17 on captured extremals, so the bar is relative to the element, not to the column)."""
+    a = {n: i for i, n in enumerate(rec['names'])}
+    b = {n: i for i, n in enumerate(g['names'])}
+    out = set(a) ^ set(b)
+    for n in set(a) & set(b):
+        i, j = a[n], b[n]
+        bad = any(rec[f][i] != g[f][j] for f in EXACT_SITE_FIELDS)
+        for f in FLOAT_SITE_FIELDS:
+            x = np.atleast_1d(np.asarray(rec[f][i], dtype=float))
+            y = np.atleast_1d(np.asarray(g[f][j], dtype=float))
+            if not np.array_equal(np.isnan(x), np.isnan(y)):
+                bad = True
+                continue
+            d = np.abs(x - y)
+            d[np.isnan(d)] = 0.
+            if np.any(d > tol * np.maximum(1., np.abs(np.where(np.isnan(y), 0., y)))):
+                bad = True
+        if bad:
+            out.add(str(n))
+    return {str(n) for n in out}

@@ -148,7 +148,8 @@ class PortSite:
 class Port:
     def __init__(self, pb, total_duration=None, max_depth=20, n_time=100, n_costate_sectors=30, t_init=None,
                  target_radius=None, abs_max_step=None, rel_max_step=0.01, max_dist=None, mode_origin=True,
-                 n_index_per_subframe=10, trimming_band_width=3, root_range=None, integrator='dopri5'):
+                 n_index_per_subframe=10, trimming_band_width=3, root_range=None, integrator='dopri5',
+                 open_window=False, external_cost_maps=None):
         self.pb = pb
         if total_duration is None:
             total_duration = 1.1 * pb.auto_time_upper_bound()
@@ -170,6 +171,13 @@ class Port:
         self.q = n_index_per_subframe
         self.band = trimming_band_width
         self.root_range = root_range
+        # open_window: `root_range` is a WINDOW of a larger fan that is solved elsewhere (the full-size GPU run): the last
+        # root of the window has no neighbour instead of wrapping to the first, so every site of the window is what the
+        # full fan computes for it (a site only ever looks at its next neighbour).  external_cost_maps: the trimming
+        # cost map of the WHOLE front per sub-frame, from that other run (the map is a global min over all triangles; the
+        # window's own triangles are checked against it and the dominated-extremal test uses it).
+        self.open_window = open_window
+        self.external_cost_maps = external_cost_maps
         self.integrator = integrator
         self.gcs = _is_gcs(pb)
         # event table (solver_ef.py:322-334)
@@ -348,6 +356,8 @@ class Port:
                                   1000 * np.array((np.cos(thetas[i]), np.sin(thetas[i]))), 0., self.n_time))
         for i, s in enumerate(roots):
             s.next_nb[0] = roots[(i + 1) % len(roots)]
+        if self.open_window:
+            roots[-1].next_nb[0] = None
         self.sites = {s.name: s for s in roots}
         return roots
 
@@ -356,6 +366,8 @@ class Port:
         born = []
         for s in list(self.sites.values()):
             nb = s.next_nb[s.check_next]
+            if nb is None:  # last root of an open window
+                continue
             reached = s.check_next
             child = None
             for k in range(s.check_next, min(s.index_t + 1, nb.index_t + 1, hi)):
@@ -466,6 +478,14 @@ class Port:
             for group in valid[start:i + 1]:
                 pool.update({id(s): s for s in group})
             cmap = self.cost_map(pool.values(), start * self.q, target)
+            if self.external_cost_maps is not None:
+                ext = np.asarray(self.external_cost_maps[i])
+                # the global map is a min over a superset of this window's triangles
+                own = np.isfinite(cmap)
+                assert np.all(ext[own] <= cmap[own] * (1 + 1e-9) + 1e-12), 'window triangles below the global cost map'
+                self.window_cells_equal = getattr(self, 'window_cells_equal', 0) + int(np.sum(np.isclose(ext[own], cmap[own], rtol=1e-9, atol=1e-12)))
+                self.window_cells = getattr(self, 'window_cells', 0) + int(own.sum())
+                cmap = ext
             self.last_cost_map = cmap
             self.cost_maps.append(cmap)
             considered = {id(s): s for s in valid[i]}

@@ -9,8 +9,15 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <atomic>
 #include <chrono>
 #include <string>
+#include <thread>
 
 // DABRY_HOSTSIM_TRACE=<file>: one "site attempts" line per free arc (lane-imbalance analysis, profiles/lane_imbalance.py)
 #include <stdio.h>
@@ -48,6 +55,139 @@ public:
     template <class T>
     void free(T* p) { ::free((void*) p); }
     void upload(void* d, const void* h, size_t n) { memcpy(d, h, n); }
+    void upload_async(void* d, const void* h, size_t n) { memcpy(d, h, n); }
+    struct CallGuard {  // one thread, one "device": nothing to serialise
+        explicit CallGuard(SerialBackend&) {}
+    };
+    template <class Fn>
+    static void destroy_locked(SerialBackend&, Fn&& destroy) { destroy(); }
+    void span_begin() { span_t0_ = now(); }
+    void span_end() { span_ms_ += now() - span_t0_; }
+    double span_collect() {
+        const double v = span_ms_;
+        span_ms_ = 0.;
+        return v;
+    }
+
+    // ---- collectives of the CPU tier: the ranks are processes of one host, the transport is a POSIX shared-memory
+    // segment named after the unique id, one mailbox per ordered pair of ranks (test double of the NCCL communicator
+    // of the product library; same call sequence, same engine code above it)
+    static constexpr size_t kMailBytes = (size_t) 1 << 20;
+    static constexpr int kMaxWorld = 8;
+    struct Mailbox {
+        std::atomic<uint64_t> written, read;
+        uint64_t bytes;
+        char data[kMailBytes];
+    };
+    struct Segment {
+        std::atomic<int> ready, attached;
+        Mailbox box[kMaxWorld][kMaxWorld];  // [src][dst]
+    };
+    struct Comm {
+        Segment* seg = nullptr;
+        int rank = 0, world = 1;
+        std::string name;
+    };
+    static int comm_rank(const Comm* c) { return c->rank; }
+    static int comm_world(const Comm* c) { return c->world; }
+    static bool comm_unique_id(void* id, std::string&) {
+        unsigned char* b = (unsigned char*) id;
+        memset(b, 0, 128);
+        FILE* f = fopen("/dev/urandom", "rb");
+        if (f) {
+            if (fread(b, 1, 16, f) != 16) b[0] = (unsigned char) getpid();
+            fclose(f);
+        }
+        return true;
+    }
+    static Comm* comm_create(int, int rank, int world, const void* id, std::string& err) {
+        if (world > kMaxWorld) {
+            err = "hostsim communicator: at most 8 ranks";
+            return nullptr;
+        }
+        char name[64] = "/dabry_hostsim_";
+        const unsigned char* b = (const unsigned char*) id;
+        for (int i = 0; i < 16; ++i) snprintf(name + 15 + 2 * i, 3, "%02x", b[i]);
+        Comm* c = new Comm;
+        c->rank = rank;
+        c->world = world;
+        c->name = name;
+        int fd = -1;
+        if (rank == 0) {
+            fd = shm_open(name, O_CREAT | O_RDWR, 0600);
+            if (fd >= 0 && ftruncate(fd, sizeof(Segment)) != 0) {
+                close(fd);
+                fd = -1;
+            }
+        } else {
+            for (int tries = 0; tries < 6000 && fd < 0; ++tries) {
+                fd = shm_open(name, O_RDWR, 0600);
+                struct stat st;
+                if (fd >= 0 && (fstat(fd, &st) != 0 || (size_t) st.st_size < sizeof(Segment))) {  // not sized yet
+                    close(fd);
+                    fd = -1;
+                }
+                if (fd < 0) std::this_thread::sleep_for(std::chrono::milliseconds(10));
+            }
+        }
+        void* p = fd >= 0 ? mmap(nullptr, sizeof(Segment), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0) : MAP_FAILED;
+        if (fd >= 0) close(fd);
+        if (p == MAP_FAILED) {
+            err = "hostsim communicator: shared memory segment unavailable";
+            delete c;
+            return nullptr;
+        }
+        c->seg = (Segment*) p;  // a fresh segment is zero-filled: counters start at 0
+        if (rank == 0) c->seg->ready.store(1);
+        while (c->seg->ready.load() == 0) std::this_thread::sleep_for(std::chrono::milliseconds(1));
+        c->seg->attached.fetch_add(1);
+        while (c->seg->attached.load() < world) std::this_thread::sleep_for(std::chrono::milliseconds(1));
+        if (rank == 0) shm_unlink(name);  // everybody holds a mapping: the name can go
+        return c;
+    }
+    static void comm_destroy(Comm* c) {
+        if (!c) return;
+        if (c->seg) munmap(c->seg, sizeof(Segment));
+        delete c;
+    }
+    static void post(Mailbox& m, const char* src, size_t n) {
+        while (m.written.load() != m.read.load()) std::this_thread::yield();
+        memcpy(m.data, src, n);
+        m.bytes = n;
+        m.written.fetch_add(1);
+    }
+    static void take(Mailbox& m, char* dst, size_t n) {
+        while (m.written.load() == m.read.load()) std::this_thread::yield();
+        memcpy(dst, m.data, n);
+        m.read.fetch_add(1);
+    }
+    // chunked so that two ranks sending to each other never wait for an empty mailbox at the same time
+    static void sendrecv(Comm* c, const void* send, int to, void* recv, int from, size_t bytes) {
+        for (size_t off = 0; off < bytes || off == 0; off += kMailBytes) {
+            const size_t n = bytes - off < kMailBytes ? bytes - off : kMailBytes;
+            post(c->seg->box[c->rank][to], (const char*) send + off, n);
+            take(c->seg->box[from][c->rank], (char*) recv + off, n);
+            if (bytes == 0) break;
+        }
+    }
+    void comm_ring_shift(Comm* c, const double* send, double* recv, int64_t n) {
+        sendrecv(c, send, (c->rank + c->world - 1) % c->world, recv, (c->rank + 1) % c->world, sizeof(double) * n);
+    }
+    void comm_allgather(Comm* c, const void* send, void* recv, size_t bytes) {
+        std::string mine((const char*) send, bytes);  // `send` may alias its own slot of `recv`
+        memcpy((char*) recv + c->rank * bytes, mine.data(), bytes);
+        for (int d = 1; d < c->world; ++d) {
+            const int to = (c->rank + d) % c->world, from = (c->rank + c->world - d) % c->world;
+            sendrecv(c, mine.data(), to, (char*) recv + from * bytes, from, bytes);
+        }
+    }
+    void comm_allreduce_min_f64(Comm* c, double* buf, int64_t n) {
+        std::vector<double> all((size_t) n * c->world);
+        comm_allgather(c, buf, all.data(), sizeof(double) * n);
+        for (int r = 0; r < c->world; ++r)
+            for (int64_t i = 0; i < n; ++i)
+                if (all[(size_t) r * n + i] < buf[i]) buf[i] = all[(size_t) r * n + i];
+    }
     void download(void* h, const void* d, size_t n) { memcpy(h, d, n); }
     // streamed grid upload: the serial double copies at once; DABRY_HOSTSIM_STREAMED=1 makes every host array count as
     // page-locked so that the CPU tier runs the windowed free arcs
@@ -101,7 +241,7 @@ private:
     }
     std::string err_;
     uint64_t launches_ = 0;
-    double t0_ = 0., t1_ = 0.;
+    double t0_ = 0., t1_ = 0., span_t0_ = 0., span_ms_ = 0.;
 };
 
 }  // namespace dabry

@@ -155,26 +155,54 @@ def compare_simple_record(rec, g, tol=FP64_TOL):
     return out
 
 
-def compare_tolerant(rec, g, tol=FP64_TOL, min_match=0.7):
-    """For the cases whose outcome in the reference hinges on the sign of rounding noise (DESIGN.md §7:
-    extremals sliding on the domain frame sit at x = +-1e-17 of a cost-map grid line; a stationary extremal on the
-    frame): arrival cost, success and solution set must still match; per-site records must match for at least
-    `min_match` of the sites both runs share."""
+def tie_set(key):
+    """Sites of `key` whose outcome in the UNMODIFIED reference changes when its right-hand side moves by <= 1 ulp
+    (tests/golden/tie_sets.json, written by oracle/tie_sensitivity.py).  Empty for most cases."""
+    import json
+    path = os.path.join(GOLDEN_DIR, 'tie_sets.json')
+    with open(path) as f:
+        cases = json.load(f)['cases']
+    return set(cases.get(key, {}).get('sites', ()))
+
+
+def compare_except_ties(rec, g, ties, tol=FP64_TOL):
+    """Everything `compare_sites_record` checks, site by site, EXCEPT on the listed tie-sensitive sites: the sites on
+    which the two runs differ must be a subset of `ties` (the reference itself flips them under a one-ulp perturbation,
+    oracle/tie_sensitivity.py); every other site - flags, indices, lengths, endpoints, checksums - must match, and so
+    must the global outcome (success, arrival cost, site count, time grid)."""
+    from dump import differing_sites
+    assert int(rec['n_sites']) == int(g['n_sites']), ('site count', int(rec['n_sites']), int(g['n_sites']))
+    assert list(rec['event_names']) == list(g['event_names'])
     assert bool(rec['success']) == bool(g['success'])
+    for f in ('total_duration', 'max_int_step'):
+        assert abs(float(rec[f]) - float(g[f])) <= tol * max(1., abs(float(g[f]))), f
+    assert scaled_diff(rec['times'], g['times']) <= tol
     gc, rc = float(g['solution_cost']), float(rec['solution_cost'])
     assert (np.isnan(gc) and np.isnan(rc)) or abs(rc - gc) <= tol * max(1., abs(gc)), ('arrival cost', rc, gc)
-    ours = {n: i for i, n in enumerate(rec['names'])}
-    theirs = {n: i for i, n in enumerate(g['names'])}
-    shared = [n for n in theirs if n in ours]
-    assert len(shared) >= min_match * max(len(ours), len(theirs)), (len(shared), len(ours), len(theirs))
-    same = 0
-    for n in shared:
-        i, j = ours[n], theirs[n]
-        if all(rec[f][i] == g[f][j] for f in ('index_t_init', 'traj_len', 'closure', 'obstacle')) and \
-                np.allclose(rec['first'][i, :4], g['first'][j, :4], rtol=1e-9, atol=1e-9):
-            same += 1
-    assert same >= min_match * len(shared), (same, len(shared))
-    return {'shared': len(shared), 'identical': same, 'ours': len(ours), 'theirs': len(theirs)}
+    differing = differing_sites(rec, g, tol)
+    outside = sorted(differing - ties)
+    assert not outside, ('sites differing outside the tie set', outside[:10], len(outside))
+    # insertion order of everything else
+    ours = [n for n in rec['names'] if n not in ties]
+    theirs = [n for n in g['names'] if n not in ties]
+    assert ours == theirs, 'site names / insertion order differ outside the tie set'
+    sol_diff = set(map(str, rec['solution_names'])) ^ set(map(str, g['solution_names']))
+    assert sol_diff <= ties, ('solution site sets differ outside the tie set', sorted(sol_diff - ties))
+    return {'differing': len(differing), 'tie_set': len(ties), 'sites': int(g['n_sites'])}
+
+
+def compare_solution_full(rec, g, tol=FP64_TOL):
+    """extrapolate_back_traj (solver_ef.py:701-749): the optimal trajectory extended back to t_init through its
+    ancestors, when both runs crown the same site (cost ties are broken by Python set order in the reference)."""
+    if 'solution_full_states' not in g or str(rec['solution_name']) != str(g['solution_name']):
+        return None
+    assert 'solution_full_states' in rec, 'traj_full of the solution site missing'
+    out = {}
+    for f in ('solution_full_times', 'solution_full_states'):
+        assert np.asarray(rec[f]).shape == np.asarray(g[f]).shape, (f, np.asarray(rec[f]).shape, np.asarray(g[f]).shape)
+        out[f] = scaled_diff(rec[f], g[f])
+        assert out[f] <= tol, (f, out[f])
+    return out
 
 
 def port_record(port):

@@ -6,11 +6,11 @@ pin the full-size run through size-independent properties:
   bit for bit, extremal i/100 of a 12.5 k fan started from the same initial costates (both through the throughput
   build of the arc kernels: batches below 16 k work items normally run the latency build, in which ptxas contracts
   multiply-adds differently - DABRY_B200_WIDE_BATCH=0 pins the build for this test);
-* the oracle (numpy/scipy, like the reference) on a handful of those theta_0 must give the same trajectories to 1e-9.
-  The synthetic 0.25 deg field carries node-scale noise, so many extremals are chaotic (a 1-ulp change of theta_0 moves
-  the endpoint by 1e-2: measured growth 1e3-1e4 per 4 grid samples) and no two fp64 implementations can agree on
-  them; the oracle comparison therefore picks the best-conditioned extremals, ranked by the distance between the
-  endpoints of theta_0-adjacent extremals of the big fan;
+* the oracle (numpy/scipy, like the reference) on 64 theta_0 spread evenly over the fan: error reported against the
+  measured conditioning of each extremal (the synthetic 0.25 deg field carries node-scale noise, part of the fan is
+  chaotic), 1e-9 wherever the amplification allows it;
+* configs 3 and 5 at full size: a window of 64 adjacent roots of the 2^19 / 500 k fan WITH its children (and, for
+  config 5, through the trimming with the obstacle and the penalty) against the oracle run on that window;
 * the arrival-time optimum over the big fan is <= the optimum over any sub-fan, and equals the minimum of the
   per-site arrival array; every flagged arrival sample really lies in the target disc;
 * determinism: two solves on the same handle give identical bits;
@@ -58,20 +58,21 @@ def test_era5_full_size_properties(cuda_lib, monkeypatch):
         for key in ('states', 'costates', 'controls', 'times'):
             assert np.array_equal(tb[key], ts[key], equal_nan=True), (key, i)
 
-    # the CPU oracle on the four best-conditioned picks that run the whole horizon (sensitivity = endpoint distance of
-    # theta_0-adjacent extremals of the big fan, d(theta_0) = 5e-6 rad)
+    # the CPU oracle on 64 picks spread evenly over the fan - whatever their conditioning.  The synthetic 0.25 deg field
+    # carries node-scale noise, so part of the fan is chaotic: the amplification A of an extremal is measured on the big
+    # fan itself (distance between the endpoints of theta_0-adjacent extremals / their d(theta_0) = 5e-6 rad, in units of
+    # the initial costate angle), and two correct fp64 implementations can only agree to ~ A x (rounding noise of ~700
+    # right-hand sides, 1e-13).  Bar: 1e-9 where A allows it, 1e-12 A beyond; lengths and capture flags equal whenever the
+    # trajectories agree to 1e-6.  The table is printed (pytest -s) and summarised in the assertion message.
     inner = pb.model.ff.ff
     if inner.grad_values is None:
         inner.compute_derivatives()
-    sens = []
-    for j in picks:
+    rows = []
+    for j in np.linspace(0, n_small - 1, 64).astype(int):
         i = int(j) * stride
         t2 = hb.trajs(i, 2, want=('states',))
-        if rec_b['n_samples'][i] == 100 and rec_b['n_samples'][i + 1] == 100:
-            sens.append((float(np.linalg.norm(t2['states'][0, 99] - t2['states'][1, 99])) / 5e-6, int(j)))
-    sens.sort()
-    assert len(sens) >= 4 and sens[3][0] < 1e3, sens[:6]
-    for _, j in sens[:4]:
+        m = int(min(rec_b['n_samples'][i], rec_b['n_samples'][i + 1]))
+        amp = float(np.linalg.norm(t2['states'][0, m - 1] - t2['states'][1, m - 1])) / 5e-6
         port = Port(pb, total, n_costate_sectors=n_small, root_range=(int(j), 1), max_depth=1)
         roots = port.make_roots()
         roots[0].p[0] = sub_costates[j].copy()
@@ -79,11 +80,19 @@ def test_era5_full_size_properties(cuda_lib, monkeypatch):
         site = roots[0]
         ts = hs.trajs(int(j), 1)
         n = int(rec_s['n_samples'][j])
-        assert n == len(site.t), (j, n, len(site.t))
         ref = np.array(site.x)
-        err = np.abs(ts['states'][0, :n] - ref).max()
-        assert err <= 1e-9 * max(1., np.abs(ref).max()), (j, err)
-        assert (rec_s['obstacle'][j] >= 0) == bool(site.obstacle_name)
+        k = min(n, len(site.t))
+        err = float(np.abs(ts['states'][0, :k] - ref[:k]).max() / max(1., np.abs(ref).max()))
+        rows.append((int(j), amp, err, n, len(site.t), int(rec_s['obstacle'][j] >= 0), int(bool(site.obstacle_name))))
+    print('\nera5 full size, oracle vs CUDA:  pick  amplification  max rel. error  len(cuda) len(oracle)')
+    for r in rows:
+        print('   %6d  %10.3g  %10.3g  %3d %3d' % r[:5])
+    tight = [r for r in rows if r[2] <= 1e-9]
+    assert len(tight) >= 32, ('fewer than half of the picks within 1e-9', len(tight))
+    for j, amp, err, n, n_ref, cap, cap_ref in rows:
+        assert err <= max(1e-9, 1e-12 * amp), ('error beyond what the conditioning explains', j, amp, err)
+        if err <= 1e-6:
+            assert n == n_ref and cap == cap_ref, ('length / capture flag', j, n, n_ref, cap, cap_ref)
 
     # arrival bookkeeping
     idx_b, cost_b = hb.arrivals(0, n_big)
@@ -153,3 +162,159 @@ def test_full_size_resampling_and_trimming_are_deterministic(cuda_lib, workload)
     else:
         assert (rec0['closure'] == 2).sum() > 0  # the trimming closed dominated extremals (SUBOPTIMAL)
         assert (rec0['obstacle'] >= 0).sum() > 0
+
+
+def _window_sites(solver, lo, cnt, span):
+    """Slots of the full-fan run whose dyadic index lies between the first and the last root of the window."""
+    rec = solver._handle.sites()
+    d = rec['dyadic']
+    inside = np.nonzero((d >= lo * span) & (d <= (lo + cnt - 1) * span) & ((rec['flags'] & 1) == 0))[0]
+    return rec, {int(d[i]): int(i) for i in inside}
+
+
+def _compare_window(port, solver, lo, cnt, tol=1e-9):
+    span = 1 << port.max_depth
+    rec, slot_of = _window_sites(solver, lo, cnt, span)
+    sites = list(port.sites.values())
+    assert sorted(slot_of) == sorted(s.index for s in sites), ('site sets differ', len(slot_of), len(sites))
+    worst = 0.
+    last_root = (lo + cnt - 1) * span
+    for s in sites:
+        i = slot_of[s.index]
+        assert solver.site_mngr.name_from_index(s.index) == s.name
+        assert rec['index_t_init'][i] == s.index_t_init and rec['n_samples'][i] == len(s.t), (s.name, rec['n_samples'][i], len(s.t))
+        assert rec['closure'][i] == (-1 if s.closure is None else s.closure), (s.name, rec['closure'][i], s.closure)
+        if s.index != last_root:  # set by the scan of the pair (site, next neighbour)
+            assert rec['neuter'][i] == (-1 if s.neuter is None else s.neuter), s.name
+        assert (rec['obstacle'][i] >= 0) == bool(s.obstacle_name), s.name
+        if s.obstacle_name:
+            assert port.event_names[rec['obstacle'][i]] == s.obstacle_name and rec['index_t_obs'][i] == s.index_t_obs
+            assert abs(rec['t_enter_obs'][i] - s.t_enter_obs) <= tol * max(1., abs(s.t_enter_obs)), s.name
+        if s.index != last_root:  # the last root of the window has no neighbour in the oracle run
+            assert rec['index_t_check_next'][i] == s.check_next, s.name
+        t = solver._handle.trajs(i, 1)
+        k0, n = s.index_t_init, len(s.t)
+        for key, ref in (('states', np.array(s.x)), ('costates', np.array(s.p)), ('controls', np.array(s.u))):
+            got = t[key][0, k0:k0 + n]
+            assert np.array_equal(np.isnan(got), np.isnan(ref)), (s.name, key)
+            scale = np.maximum(1., np.nanmax(np.abs(np.where(np.isnan(ref), 0., ref)), axis=0))
+            err = np.nanmax(np.abs(got - ref) / scale) if np.any(~np.isnan(ref)) else 0.
+            worst = max(worst, float(err))
+            assert err <= tol, (s.name, key, float(err))
+    return len(sites), worst
+
+
+@pytest.mark.gpu
+def test_planar_full_size_windows_against_oracle(cuda_lib):
+    """BASELINE config 3 at full size (1024 x 1024 x 48 grid, 2^19 roots, max_depth 4, ~1 M extremals): two windows of 64
+    adjacent roots WITH the children the resampling inserts between them, site by site against the oracle solving just
+    that window (open window: the last root has no neighbour, so every site is what the full fan computes)."""
+    import bench
+    from dabry_b200.solver_ef import SolverEFResampling
+    from solver_port import Port
+    pb, total, kw, _ = bench.build_problem('planar')
+    n_roots = bench.default_roots('planar')
+    s = SolverEFResampling(pb, total, n_costate_sectors=n_roots, max_sites=int(2.5 * n_roots) + 4096, **kw)
+    s.solve()
+    inner = pb.model.ff.ff
+    if inner.grad_values is None:
+        inner.compute_derivatives()
+    total_sites, children = 0, 0
+    # theta_0 = pi heads straight at the target (the control is -p / |p|); the second window looks across the flow
+    for lo in (n_roots // 2 - 32, 100_000):
+        port = Port(pb, total, n_costate_sectors=n_roots, root_range=(lo, 64), open_window=True, **kw)
+        port.run_resampling()
+        n, worst = _compare_window(port, s, lo, 64)
+        total_sites += n
+        children += n - 64
+        print('planar window at root %d: %d sites (%d children), worst relative error %.2e' % (lo, n, n - 64, worst))
+    assert children > 0, 'the windows contain no refinement: the test does not exercise the resampling'
+    s.close()
+
+
+@pytest.mark.gpu
+def test_regional_full_size_window_through_trimming(cuda_lib):
+    """BASELINE config 5 at full size (regional spherical grid, circular obstacle + penalty, SolverEFTrimming, 500 k
+    roots): a window of 64 adjacent roots aimed at the target, with children, through all ten trimming sub-frames.  The
+    trimming cost map is a global min over the whole front, so the oracle of the window takes the per-sub-frame maps of
+    the full-fan run for its dominated-extremal test - after checking that they are nowhere above what the window's own
+    triangles give (and equal where the window dominates)."""
+    import bench
+    from dabry_b200.solver_ef import SolverEFTrimming
+    from solver_port import Port
+    pb, total, kw, _ = bench.build_problem('regional')
+    kw.pop('trimming')
+    n_roots = bench.default_roots('regional')
+    s = SolverEFTrimming(pb, total, n_costate_sectors=n_roots, max_sites=int(2.5 * n_roots) + 4096, **kw)
+    s.setup()
+    maps = []
+    for _ in range(s.n_subframes):
+        s.step()
+        maps.append(s._handle.cost_map(100, 100, full=False))
+    s.check_solutions()
+    inner = pb.model.ff.ff
+    if inner.grad_values is None:
+        inner.compute_derivatives()
+    # costate angle of the extremal that starts straight at the target: heading + pi
+    d = np.asarray(pb.x_target) - np.asarray(pb.x_init)
+    theta = (np.arctan2(d[1], d[0]) + np.pi) % (2 * np.pi)
+    lo = int(theta / (2 * np.pi) * n_roots) - 32
+    port = Port(pb, total, n_costate_sectors=n_roots, root_range=(lo, 64), open_window=True, external_cost_maps=maps, **kw)
+    port.run_trimming()
+    n, worst = _compare_window(port, s, lo, 64)
+    print('regional window at root %d: %d sites (%d children), worst relative error %.2e; cost-map cells of the window equal to '
+          'the global map: %d of %d' % (lo, n, n - 64, worst, port.window_cells_equal, port.window_cells))
+    assert port.window_cells > 0
+    closed = sum(1 for x in port.sites.values() if x.closure == 2)
+    print('   window sites closed SUBOPTIMAL by the trimming: %d' % closed)
+    s.close()
+
+
+def test_window_oracle_logic_small_planar(hostsim):
+    """The window comparison itself, at small size on the CPU tier (tests/hostsim): a fan of 1 024 roots on the reduced
+    planar grid, two open windows of 16 roots with their children against the oracle of each window."""
+    import bench
+    from dabry_b200.solver_ef import SolverEFResampling
+    from solver_port import Port
+    pb, total, kw, _ = bench.build_problem('planar', small=True)
+    s = SolverEFResampling(pb, total, n_costate_sectors=1024, **kw)
+    s.solve()
+    inner = pb.model.ff.ff
+    if inner.grad_values is None:
+        inner.compute_derivatives()
+    children = 0
+    for lo in (504, 200):
+        port = Port(pb, total, n_costate_sectors=1024, root_range=(lo, 16), open_window=True, **kw)
+        port.run_resampling()
+        n, _ = _compare_window(port, s, lo, 16)
+        children += n - 16
+    assert children > 0
+    s.close()
+
+
+def test_window_oracle_logic_small_trimming(hostsim):
+    """The same for the trimming variant with the global cost maps handed to the window oracle (reduced regional grid,
+    obstacle + penalty, 512 roots, window of 16 aimed at the target)."""
+    import bench
+    from dabry_b200.solver_ef import SolverEFTrimming
+    from solver_port import Port
+    pb, total, kw, _ = bench.build_problem('regional', small=True)
+    kw.pop('trimming')
+    s = SolverEFTrimming(pb, total, n_costate_sectors=512, **kw)
+    s.setup()
+    maps = []
+    for _ in range(s.n_subframes):
+        s.step()
+        maps.append(s._handle.cost_map(100, 100, full=False))
+    s.check_solutions()
+    inner = pb.model.ff.ff
+    if inner.grad_values is None:
+        inner.compute_derivatives()
+    d = np.asarray(pb.x_target) - np.asarray(pb.x_init)
+    theta = (np.arctan2(d[1], d[0]) + np.pi) % (2 * np.pi)
+    lo = int(theta / (2 * np.pi) * 512) - 8
+    port = Port(pb, total, n_costate_sectors=512, root_range=(lo, 16), open_window=True, external_cost_maps=maps, **kw)
+    port.run_trimming()
+    n, _ = _compare_window(port, s, lo, 16)
+    assert port.window_cells > 0 and n >= 16
+    s.close()

@@ -13,9 +13,12 @@ import pytest
 import parity_util as pu
 from dump import solver_record
 
-# Cases whose reference outcome depends on the sign of 1e-17 rounding noise: extremals sliding on the
-# domain frame sit within +-1e-17 of the outermost cost-map grid line, so border cells of the trimming cost map
-# flip between inf and finite; `trap` has a root extremal pinned on the frame by an opposing flow of exactly srf.
+# Cases in which some sites of the reference's OWN result depend on the sign of 1e-17 rounding noise:
+# extremals sliding on the domain frame sit within +-1e-17 of the outermost cost-map grid line, so border cells of the
+# trimming cost map flip between inf and finite; `trap` has a root extremal pinned on the frame by an opposing flow of
+# exactly srf.  Proven on the reference itself: oracle/tie_sensitivity.py moves the reference's right-hand side by
+# <= 1 ulp and lists the sites whose record changes (tests/golden/tie_sets.json).  These cases are compared site by
+# site on everything OUTSIDE that list (parity_util.compare_except_ties); all other cases are compared exactly.
 TIE_SENSITIVE = {'trap_R', 'chertovskih_T', 'gyre_T', 'gyre_rhoads2010_T', 'linear_T', 'moving_vortex_T',
                  'obstacle_T', 'point_symmetric_techy2011_T', 'spherical_geodesic_T', 'three_vortices_T', 'trap_T'}
 
@@ -29,11 +32,14 @@ def _check_site_case(key):
     rec = solver_record(solver, full=case.full and 'traj_offsets' in g)
     try:
         if key in TIE_SENSITIVE:
-            pu.compare_tolerant(rec, g)
+            out = pu.compare_except_ties(rec, g, pu.tie_set(key))
+            # the escape hatch stays small: most sites are compared even in these cases
+            assert out['tie_set'] <= 0.4 * out['sites'], out
         else:
             pu.compare_sites_record(rec, g)
             if 'traj_offsets' in rec and 'traj_offsets' in g:
                 pu.compare_full_trajectories(rec, g)
+        pu.compare_solution_full(rec, g)  # extrapolate_back_traj (A15)
         stats = solver.native_stats()
         assert stats['rk_steps'] > 0 and stats['kernel_launches'] > 0
         # step count parity with the reference's own nfev bookkeeping: (nfev - 2) / 6 per solve_ivp call
