@@ -598,8 +598,18 @@ class Workload:
         dist.all_gather(gathered, t_own)
         nb = (ctx.rank + 1) % ctx.world
         first = nb * self.shard_block if self.shard_block else self.root_range_of(nb)[0]
-        s = self.make_solver(device_roots=True, root_range=(first, n), max_sites=n + 4096)
-        s.solve()
+        # same build of the arc kernels as the big fan: small batches normally run the latency build, in which ptxas
+        # contracts multiply-adds differently - DABRY_B200_WIDE_BATCH=0 pins the throughput build
+        prev = os.environ.get('DABRY_B200_WIDE_BATCH')
+        os.environ['DABRY_B200_WIDE_BATCH'] = '0'
+        try:
+            s = self.make_solver(device_roots=True, root_range=(first, n), max_sites=n + 4096)
+            s.solve()
+        finally:
+            if prev is None:
+                del os.environ['DABRY_B200_WIDE_BATCH']
+            else:
+                os.environ['DABRY_B200_WIDE_BATCH'] = prev
         h = s._handle
         rec2 = h.sites(0, n)
         again = np.concatenate((h.trajs(0, n, want=('states',))['states'].reshape(n, -1),

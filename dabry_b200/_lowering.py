@@ -34,7 +34,7 @@ def apply_flow(handle, ff, shared=False):
         # host-supplied Jacobian samples (DiscreteFF.from_ff) are uploaded; the default central differences
         # (flowfield.py:474-504) are recomputed on the device instead of being shipped
         grad = None
-        if inner.grad_values is not None and not getattr(inner, '_grad_is_default', False):
+        if inner.grad_values is not None and not inner.grad_is_device_default():
             grad = nat.f64(inner.grad_values)
         b = np.asarray(inner.bounds, dtype=float)
         lo = nat.f64(np.concatenate(((0.,), b[:, 0])) if not unsteady else b[:, 0])
@@ -119,3 +119,31 @@ def flow_evaluator(ff, device=0):
     handle = nat.Handle(cfg, keepalive=(times,))
     apply_flow(handle, ff)
     return handle
+
+
+def time_upper_bound(pb, rel_timeout=10, device=0):
+    """(time_orthodromic, time_htarget) of `pb` (problem.py:193-239): the two feedback flights of the time-horizon
+    heuristic, integrated on the device (dabry_time_upper_bound) over the window the reference uses,
+    [ff.t_start, ff.t_start + rel_timeout * length_reference / srf_max]."""
+    cfg = nat.Config()
+    cfg.abi_version = nat.ABI_VERSION
+    cfg.coords = coords_code(pb.coords)
+    cfg.n_time, cfg.max_depth, cfg.mode_origin = 2, 1, 1
+    cfg.device = device
+    cfg.n_index_per_subframe, cfg.trimming_band_width = 10, 3
+    cfg.cost_map_nx = cfg.cost_map_ny = 2
+    cfg.n_roots = cfg.root_count = 1
+    cfg.max_step, cfg.rtol, cfg.atol = 1., 1e-3, 1e-6  # solve_ivp defaults (rk.py:86)
+    cfg.srf = pb.srf_max
+    cfg.x_target[0], cfg.x_target[1] = pb.x_target
+    cfg.target_radius = pb.target_radius
+    t0 = float(pb.model.ff.t_start)
+    t_end = float(np.linspace(t0, t0 + rel_timeout * pb.length_reference / pb.srf_max, 1000)[-1])
+    times = nat.f64(np.array((t0, t_end)))
+    cfg.times = nat.dptr(times)
+    handle = nat.Handle(cfg, keepalive=(times,))
+    try:
+        apply_flow(handle, pb.model.ff)
+        return handle.time_upper_bound(pb.x_init, t0, t_end)
+    finally:
+        handle.close()

@@ -137,6 +137,7 @@ SIGNATURES = {
                                              c_double_p, C.POINTER(Wrapper)]),
     'dabry_solve_sharded': (C.c_int, [_H, C.c_int32, c_double_p]),
     'dabry_get_global_solution': (C.c_int, [_H, c_double_p, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]),
+    'dabry_time_upper_bound': (C.c_int, [_H, c_double_p, C.c_double, C.c_double, c_double_p]),
     'dabry_eval_rhs': (C.c_int, [_H, C.c_int64, c_double_p, c_double_p, c_double_p]),
     'dabry_eval_flow': (C.c_int, [_H, C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p]),
 }
@@ -384,6 +385,12 @@ class Handle:
         out = np.empty((nx, ny))
         self.call('dabry_get_cost_map', 1 if full else 0, dptr(out))
         return out
+
+    def time_upper_bound(self, x_init, t_start, t_end):
+        x = f64(np.asarray(x_init, dtype=float).reshape(2))
+        out = np.empty(2)
+        self.call('dabry_time_upper_bound', dptr(x), float(t_start), float(t_end), dptr(out))
+        return float(out[0]), float(out[1])
 
     def eval_rhs(self, t, y):
         t, y = f64(np.atleast_1d(t)), f64(np.atleast_2d(y))

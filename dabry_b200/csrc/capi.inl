@@ -336,6 +336,12 @@ int dabry_get_global_solution(dabry_solver* h, double* cost, int32_t* owner_rank
     return DABRY_OK;
 }
 
+int dabry_time_upper_bound(dabry_solver* h, const double x_init[2], double t_start, double t_end, double out[2]) {
+    DABRY_GUARD(h);
+    if (!x_init || !out) return DABRY_ERR_INVALID;
+    return E.time_upper_bound(x_init, t_start, t_end, out);
+}
+
 int dabry_eval_rhs(dabry_solver* h, int64_t n, const double* t, const double* y, double* dy) {
     DABRY_GUARD(h);
     if (n <= 0) return DABRY_OK;

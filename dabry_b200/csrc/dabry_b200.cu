@@ -197,7 +197,7 @@ private:
         cudaEvent_t ready;
     };
     DeviceBlockCache() {
-        limit_ = (size_t) 96 << 30;
+        limit_ = (size_t) 32 << 30;  // per device; DABRY_B200_CACHE_MB overrides (a 10 M-extremal store is 61 GB)
         if (const char* env = getenv("DABRY_B200_CACHE_MB")) limit_ = (size_t) strtoull(env, nullptr, 10) << 20;
     }
     std::mutex mutex_;

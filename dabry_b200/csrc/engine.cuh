@@ -176,6 +176,23 @@ struct FreeArcPhase {  // the hot kernel: one thread per extremal, free arc with
     }
 };
 
+// Tiny batches (the reference's own 30-root cases: a resampling round integrates a few dozen children) are bound by the
+// latency of one warp: 32 extremals in different branches of the field, the event handling and the step control
+// serialise on it (ncu on `movor`: 12.7 of 32 lanes active per instruction).  Spread<Phase> gives every work item a warp
+// of its own (lane 0 works, 31 lanes idle): the GPU has 4 700 warp slots, a round of a small case needs tens.
+#ifndef DABRY_SPREAD_BATCH  // work items up to which an arc kernel runs one extremal per warp
+#define DABRY_SPREAD_BATCH 2048
+#endif
+template <class Phase>
+struct Spread {
+    static constexpr int kThreads = 32;
+    static constexpr int kMinBlocks = 1;
+    Phase inner;
+    DABRY_HD void operator()(int64_t i) const {
+        if ((i & 31) == 0) inner(i >> 5);
+    }
+};
+
 struct CapturedFlagPhase {  // which work items need the obstacle kernel
     static constexpr int kThreads = 256;
     SiteStore S;
@@ -358,6 +375,19 @@ struct EvalFlowPhase {
         jac[4 * i + 1] = f.j01;
         jac[4 * i + 2] = f.j10;
         jac[4 * i + 3] = f.j11;
+    }
+};
+
+template <int FK>
+struct TimeBoundPhase {  // auto_time_upper_bound: work item 0 = orthodromic flight, 1 = heading-to-target flight
+    static constexpr int kThreads = 32;
+    double x0, x1, t_start, t_end;
+    double* out;
+    Counters* counters;
+    DABRY_HD void operator()(int64_t i) const {
+        unsigned attempts = 0;
+        out[i] = feedback_flight_time<FK>(problem(), (int) i, x0, x1, t_start, t_end, attempts);
+        counter_add(&counters->spare1, attempts);
     }
 };
 
@@ -578,6 +608,8 @@ public:
         memset(&stats, 0, sizeof(stats));
         if (const char* env = getenv("DABRY_FREE_CHUNK")) free_chunk = atoi(env);
         if (const char* env = getenv("DABRY_B200_WIDE_BATCH")) wide_batch = atoll(env);
+        if (const char* env = getenv("DABRY_B200_SPREAD_BATCH")) spread_batch = atoll(env);
+        if (spread_batch > wide_batch) spread_batch = wide_batch;  // WIDE_BATCH=0 pins every batch to the lean build
         if (const char* env = getenv("DABRY_B200_VERIFY_ARRIVALS")) verify_arrivals = atoi(env) != 0;
         if (const char* env = getenv("DABRY_B200_STREAM_UPLOAD")) stream_upload = atoi(env);
         times_h.assign(c.times, c.times + c.n_time);
@@ -1285,6 +1317,22 @@ public:
     int32_t global_owner = -1;
     uint64_t global_rk_steps = 0;
 
+    // NavigationProblem.auto_time_upper_bound (problem.py:193-239): out[0] = time_orthodromic, out[1] = time_htarget
+    int time_upper_bound(const double* x_init, double t_start, double t_end, double* out) {
+        bind();
+        if (P.field.kind < 0) return fail(DABRY_ERR_INVALID, "no flow field set");
+        double* d = (double*) scratch(sizeof(double) * 2);
+        if (!d) return fail(DABRY_ERR_CAPACITY, "out of device memory");
+        const double scipy_rtol = P.rtol, scipy_atol = P.atol;
+        (void) scipy_rtol;
+        (void) scipy_atol;
+        if (P.field.kind == FIELD_GRID) be.launch(2, TimeBoundPhase<FIELD_GRID>{x_init[0], x_init[1], t_start, t_end, d, d_counters});
+        else if (P.field.kind == FIELD_GRID_F32) be.launch(2, TimeBoundPhase<FIELD_GRID_F32>{x_init[0], x_init[1], t_start, t_end, d, d_counters});
+        else be.launch(2, TimeBoundPhase<FIELD_PROGRAM>{x_init[0], x_init[1], t_start, t_end, d, d_counters});
+        be.download(out, d, sizeof(double) * 2);
+        return check();
+    }
+
     // ---- evaluation hooks ----
     int eval_rhs(int64_t n, const double* t, const double* y, double* dy) {
         bind();
@@ -1352,6 +1400,7 @@ private:
     // work items up to which the latency build of the arc kernels is launched.  The two builds differ in how ptxas
     // contracts multiply-adds (<= 1 ulp per operation); DABRY_B200_WIDE_BATCH=0 pins every batch to the lean build
     int64_t wide_batch = DABRY_WIDE_BATCH;
+    int64_t spread_batch = DABRY_SPREAD_BATCH;  // <= : one extremal per warp (Spread); DABRY_B200_SPREAD_BATCH overrides
     bool verify_arrivals = false;
     // streamed grid upload (set_flow_grid / pack_groups / integrate); DABRY_B200_STREAM_UPLOAD=0 disables it
     int stream_upload = 1;  // 0: never, 1: grids of 64 MB and more, 2: every eligible grid (tests)
@@ -1457,70 +1506,76 @@ private:
         return DABRY_OK;
     }
 
+    // One array of the site store during a re-pitch: where the pointer lives, element size, [rows][capacity * per] shape
+    struct StoreArray {
+        void** slot;
+        size_t elem;
+        int64_t rows, per;
+        int fill_ones;  // fresh memory = all-ones bytes (NaN controls, -1 links)
+        void* fresh;
+    };
     template <class T>
-    bool grow(T*& p, int64_t old_cap, int64_t new_cap, int64_t rows, int64_t per) {
-        // [rows][cap * per] arrays: re-pitch row by row
-        T* q = (T*) be.alloc(sizeof(T) * rows * new_cap * per);
-        if (!q) return false;
-        if (p && n_sites > 0)
-            be.copy2d(q, sizeof(T) * new_cap * per, p, sizeof(T) * old_cap * per, sizeof(T) * n_sites * per, rows);
-        be.free(p);
-        p = q;
-        return true;
+    static StoreArray store_array(T*& p, int64_t rows, int64_t per, int fill_ones = 0) {
+        return StoreArray{reinterpret_cast<void**>(&p), sizeof(T), rows, per, fill_ones, nullptr};
     }
 
     void free_store(SiteStore& s) {
-        be.free(s.xp); be.free(s.ctrl); be.free(s.tt); be.free(s.cost0); be.free(s.t_enter_obs);
-        be.free(s.index_t_init); be.free(s.n_samples); be.free(s.closure); be.free(s.neuter);
-        be.free(s.index_neutered); be.free(s.obstacle); be.free(s.index_t_obs); be.free(s.trigo);
-        be.free(s.check_next); be.free(s.depth); be.free(s.flags); be.free(s.parent_prev); be.free(s.parent_next);
-        be.free(s.created_subframe); be.free(s.valid_first); be.free(s.valid_last); be.free(s.dyadic);
-        be.free(s.next_nb); be.free(s.n_target_events); be.free(s.t_target_events); be.free(s.ivp_status);
-        be.free(s.arc_from); be.free(s.enter); be.free(s.arr_index); be.free(s.arr_cost);
-        be.free(s.carry_t); be.free(s.carry_h); be.free(s.carry_y); be.free(s.carry_f); be.free(s.carry_g);
-        be.free(s.carry_eval_i);
+        for (StoreArray& a : store_arrays(s)) {
+            be.free((char*) *a.slot);
+            *a.slot = nullptr;
+        }
     }
 
+    std::vector<StoreArray> store_arrays(SiteStore& s) {
+        const int64_t T = cfg.n_time;
+        return {
+            store_array(s.xp, T, 1), store_array(s.ctrl, T, 1, 1), store_array(s.tt, T, 1), store_array(s.next_nb, T, 1, 1),
+            store_array(s.cost0, 1, 1), store_array(s.t_enter_obs, 1, 1), store_array(s.index_t_init, 1, 1),
+            store_array(s.n_samples, 1, 1), store_array(s.closure, 1, 1), store_array(s.neuter, 1, 1),
+            store_array(s.index_neutered, 1, 1), store_array(s.obstacle, 1, 1), store_array(s.index_t_obs, 1, 1),
+            store_array(s.trigo, 1, 1), store_array(s.check_next, 1, 1), store_array(s.depth, 1, 1),
+            store_array(s.flags, 1, 1), store_array(s.parent_prev, 1, 1), store_array(s.parent_next, 1, 1),
+            store_array(s.created_subframe, 1, 1), store_array(s.valid_first, 1, 1), store_array(s.valid_last, 1, 1),
+            store_array(s.dyadic, 1, 1), store_array(s.n_target_events, 1, 1),
+            store_array(s.t_target_events, 1, DABRY_MAX_TARGET_EVENTS), store_array(s.ivp_status, 1, 1),
+            store_array(s.arc_from, 1, 1), store_array(s.enter, 1, 1), store_array(s.arr_index, 1, 1),
+            store_array(s.arr_cost, 1, 1), store_array(s.carry_t, 1, 1), store_array(s.carry_h, 1, 1),
+            store_array(s.carry_y, 1, 1), store_array(s.carry_f, 1, 1), store_array(s.carry_g, 1, DABRY_MAX_EVENTS),
+            store_array(s.carry_eval_i, 1, 1),
+        };
+    }
+
+    // Grow the site store to at least `want` slots.  Every new array is allocated FIRST; only when all allocations have
+    // succeeded are the rows re-pitched and the pointers and the capacity committed, so an out-of-memory failure leaves
+    // the store as it was (old pitch, old capacity).
     int reserve(int64_t want) {
         if (want <= S.capacity) return DABRY_OK;
         if (want > INT_MAX / 2) return fail(DABRY_ERR_CAPACITY, "more than 2^30 sites");
         int64_t cap = S.capacity > 0 ? S.capacity + S.capacity / 2 : want;
         if (cap < want) cap = want;
         cap = (cap + 31) / 32 * 32;  // keep rows 256-byte aligned
-        const int64_t oc = S.capacity, T = cfg.n_time;
+        const int64_t oc = S.capacity;
+        std::vector<StoreArray> arrays = store_arrays(S);
         bool ok = true;
-        // controls and neighbour links start as NaN / -1 everywhere (free arcs never write controls)
-        Control* nctrl = (Control*) be.alloc(sizeof(Control) * T * cap);
-        int32_t* nnb = (int32_t*) be.alloc(sizeof(int32_t) * T * cap);
-        if (!nctrl || !nnb) return fail(DABRY_ERR_CAPACITY, "out of device memory (site store)");
-        be.fill_ones(nctrl, sizeof(Control) * T * cap);  // NaN controls, -1 links (all-ones bytes)
-        be.fill_ones(nnb, sizeof(int32_t) * T * cap);
-        if (S.ctrl && n_sites > 0) {
-            be.copy2d(nctrl, sizeof(Control) * cap, S.ctrl, sizeof(Control) * oc, sizeof(Control) * n_sites, T);
-            be.copy2d(nnb, sizeof(int32_t) * cap, S.next_nb, sizeof(int32_t) * oc, sizeof(int32_t) * n_sites, T);
+        for (StoreArray& a : arrays) {
+            a.fresh = be.alloc(a.elem * a.rows * cap * a.per);
+            if (!a.fresh) {
+                ok = false;
+                break;
+            }
         }
-        be.free(S.ctrl);
-        be.free(S.next_nb);
-        S.ctrl = nctrl;
-        S.next_nb = nnb;
-        ok = ok && grow(S.xp, oc, cap, T, 1) && grow(S.tt, oc, cap, T, 1);
-        ok = ok && grow(S.cost0, oc, cap, 1, 1) && grow(S.t_enter_obs, oc, cap, 1, 1);
-        ok = ok && grow(S.index_t_init, oc, cap, 1, 1) && grow(S.n_samples, oc, cap, 1, 1);
-        ok = ok && grow(S.closure, oc, cap, 1, 1) && grow(S.neuter, oc, cap, 1, 1);
-        ok = ok && grow(S.index_neutered, oc, cap, 1, 1) && grow(S.obstacle, oc, cap, 1, 1);
-        ok = ok && grow(S.index_t_obs, oc, cap, 1, 1) && grow(S.trigo, oc, cap, 1, 1);
-        ok = ok && grow(S.check_next, oc, cap, 1, 1) && grow(S.depth, oc, cap, 1, 1);
-        ok = ok && grow(S.flags, oc, cap, 1, 1) && grow(S.parent_prev, oc, cap, 1, 1);
-        ok = ok && grow(S.parent_next, oc, cap, 1, 1) && grow(S.created_subframe, oc, cap, 1, 1);
-        ok = ok && grow(S.valid_first, oc, cap, 1, 1) && grow(S.valid_last, oc, cap, 1, 1);
-        ok = ok && grow(S.dyadic, oc, cap, 1, 1) && grow(S.n_target_events, oc, cap, 1, 1);
-        ok = ok && grow(S.t_target_events, oc, cap, 1, DABRY_MAX_TARGET_EVENTS) && grow(S.ivp_status, oc, cap, 1, 1);
-        ok = ok && grow(S.arc_from, oc, cap, 1, 1) && grow(S.enter, oc, cap, 1, 1);
-        ok = ok && grow(S.arr_index, oc, cap, 1, 1) && grow(S.arr_cost, oc, cap, 1, 1);
-        ok = ok && grow(S.carry_t, oc, cap, 1, 1) && grow(S.carry_h, oc, cap, 1, 1) && grow(S.carry_y, oc, cap, 1, 1);
-        ok = ok && grow(S.carry_f, oc, cap, 1, 1) && grow(S.carry_g, oc, cap, 1, DABRY_MAX_EVENTS);
-        ok = ok && grow(S.carry_eval_i, oc, cap, 1, 1);
-        if (!ok) return fail(DABRY_ERR_CAPACITY, "out of device memory (site store)");
+        if (!ok) {
+            for (StoreArray& a : arrays) be.free((char*) a.fresh);
+            return fail(DABRY_ERR_CAPACITY, "out of device memory (site store)");
+        }
+        for (StoreArray& a : arrays) {
+            // controls and neighbour links start as NaN / -1 everywhere (free arcs never write controls)
+            if (a.fill_ones) be.fill_ones(a.fresh, a.elem * a.rows * cap * a.per);
+            if (*a.slot && n_sites > 0)  // [rows][cap * per] arrays: re-pitch row by row
+                be.copy2d(a.fresh, a.elem * cap * a.per, *a.slot, a.elem * oc * a.per, a.elem * n_sites * a.per, a.rows);
+            be.free((char*) *a.slot);
+            *a.slot = a.fresh;
+        }
         S.capacity = (int32_t) cap;
         S.n_time = cfg.n_time;
         S.t_init = cfg.t_init;
@@ -1564,6 +1619,9 @@ private:
                 if (free_chunk > 0)
                     be.launch(n_cur, FreeArcPhase<kField, kMethod, true>{S, cur, cur_base, index_t, free_chunk,
                                                                          d_counters, d_captured});
+                else if (n_cur <= spread_batch)
+                    be.launch(n_cur * 32, Spread<FreeArcPhase<kField, kMethod, false, false>>{
+                                              {S, cur, cur_base, index_t, 0, d_counters, d_captured}});
                 else if (n_cur <= wide_batch)
                     be.launch(n_cur, FreeArcPhase<kField, kMethod, false, false>{S, cur, cur_base, index_t, 0,
                                                                                  d_counters, d_captured});
@@ -1586,7 +1644,10 @@ private:
             if (n_cap > 0) {
                 dispatch_field(rk4, [&](auto fk, auto method) {
                     constexpr int kField = decltype(fk)::value, kMethod = decltype(method)::value;
-                    if (n_cap <= wide_batch)
+                    if (n_cap <= spread_batch)
+                        be.launch(n_cap * 32, Spread<ObstacleArcPhase<kField, kMethod, false>>{
+                                                  {S, list, d_cap_list, base, index_t, d_counters}});
+                    else if (n_cap <= wide_batch)
                         be.launch(n_cap, ObstacleArcPhase<kField, kMethod, false>{S, list, d_cap_list, base, index_t,
                                                                                   d_counters});
                     else

@@ -16,6 +16,11 @@
 #pragma once
 #include "common.cuh"
 
+// 1: the hot kernel fetches the grid cell of a warp cooperatively through shared memory (grid_eval below)
+#ifndef DABRY_COOP_FETCH
+#define DABRY_COOP_FETCH 0
+#endif
+
 namespace dabry {
 
 // FIELD_GRID_F32: the same pair records stored in fp32 (48 B per node, three 16-byte loads); arithmetic stays fp64
@@ -323,12 +328,55 @@ DABRY_HD void grid_eval(const GridDesc& G, double t, double x0, double x1, Flow&
             acc[2 * c + 1] = (double) (ft_lo * lo1 + ft_hi * hi1);
         }
     } else {
+#if defined(__CUDA_ARCH__) && DABRY_COOP_FETCH
+        if (JAC) {
+            // Warp-cooperative cell fetch (north star: shared-memory staging of grid tiles for theta-sorted bundles).
+            // The extremals of a warp are theta_0-neighbours: nearly always they sit in the same cell of the same pair of
+            // frames, so the 24 sixteen-byte pieces of that cell are fetched ONCE per warp - one cp.async per lane into a
+            // 384-byte tile of the warp in shared memory, all in flight at once and landing in no register - and every
+            // lane then reads them as shared-memory broadcasts.  Lanes in another cell (a warp straddling a cell edge, a
+            // lane that rejected a step and sits in the next frame) are served by further rounds of the same loop.
+            __shared__ __align__(16) double2 coop_tile[4][24];  // arc kernels: at most 4 warps per block
+            const unsigned active = __activemask();
+            const int lane = threadIdx.x & 31;
+            double2* tile = coop_tile[(threadIdx.x >> 5) & 3];
+            const unsigned k00 = row0 + j0, k01 = row0 + j1, k10 = row1 + j0, k11 = row1 + j1;
+            const int rank = __popc(active & ((1u << lane) - 1u)), n_active = __popc(active);
+            unsigned pending = active;
+            while (pending) {
+                const int leader = __ffs(pending) - 1;
+                const unsigned l00 = __shfl_sync(active, k00, leader), l01 = __shfl_sync(active, k01, leader);
+                const unsigned l10 = __shfl_sync(active, k10, leader), l11 = __shfl_sync(active, k11, leader);
+                const bool mine = ((pending >> lane) & 1u) && k00 == l00 && k11 == l11;
+                for (int p = rank; p < 24; p += n_active) {
+                    const unsigned node = p < 6 ? l00 : (p < 12 ? l01 : (p < 18 ? l10 : l11));
+                    const double* src = G.data + (size_t) node * 12 + 2 * (p % 6);
+                    const unsigned dst = (unsigned) __cvta_generic_to_shared(tile + p);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                }
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                __syncwarp(active);
+                if (mine) {
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) {
+                        const double2 a = tile[c], b = tile[6 + c], d = tile[12 + c], e = tile[18 + c];
+                        const double lo = ((w00 * a.x + w01 * b.x) + w10 * d.x) + w11 * e.x;
+                        const double hi = ((w00 * a.y + w01 * b.y) + w10 * d.y) + w11 * e.y;
+                        acc[c] = wt_lo * lo + wt_hi * hi;
+                    }
+                }
+                __syncwarp(active);
+                pending &= ~__ballot_sync(active, mine);
+            }
+        } else
+#endif
+        {
         const double* n00 = G.data + (size_t) (row0 + j0) * 12;
         const double* n01 = G.data + (size_t) (row0 + j1) * 12;
         const double* n10 = G.data + (size_t) (row1 + j0) * 12;
         const double* n11 = G.data + (size_t) (row1 + j1) * 12;
-        // Measured on B200 and dropped: staging the 24 pieces in shared memory with cp.async (3x slower:
-        // the 48 KB per block shrink the L1 the integrator's spills live in), ordered inline-PTX loads (ptxas
+        // Measured on B200 and dropped: staging the 24 pieces PER THREAD in shared memory with cp.async (3x
+        // slower: the 48 KB per block shrink the L1 the integrator's spills live in), ordered inline-PTX loads (ptxas
         // re-schedules them), and prefetch.global.L1 of the cell ahead of the latitude trigonometry (+6 %).
 #pragma unroll
         for (int c = 0; c < (JAC ? 6 : 2); ++c) {
@@ -337,6 +385,7 @@ DABRY_HD void grid_eval(const GridDesc& G, double t, double x0, double x1, Flow&
             const double lo = ((w00 * a.x + w01 * b.x) + w10 * d.x) + w11 * e.x;
             const double hi = ((w00 * a.y + w01 * b.y) + w10 * d.y) + w11 * e.y;
             acc[c] = wt_lo * lo + wt_hi * hi;
+        }
         }
     }
     o.w0 = acc[0];

@@ -202,7 +202,8 @@ DABRY_HD void solve_ivp(const Rhs& rhs, Events& events, Sink& sink, double t0, d
         int na = 0;
         for (int e = 0; e < ne; ++e) {
             const double g_new = events.value(e, t, S.y);
-            if (g[e] >= 0. && g_new <= 0.) act[na++] = e;
+            // find_active_events (ivp.py:134-158): direction -1, or 0 (either way) for the feedback flights
+            if ((g[e] >= 0. && g_new <= 0.) || (Events::kBothDirections && g[e] <= 0. && g_new >= 0.)) act[na++] = e;
             g[e] = g_new;
         }
         // the local interpolant is needed for event roots and for the t_eval samples inside this step

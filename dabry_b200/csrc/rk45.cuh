@@ -8,6 +8,10 @@
 
 namespace dabry {
 
+#ifndef DABRY_TRACE_RK_ATTEMPT  // analysis hook of tests/hostsim (one line per step attempt); nothing in the product
+#define DABRY_TRACE_RK_ATTEMPT(n, t, h, error_norm)
+#endif
+
 #define DABRY_RK_SAFETY 0.9
 #define DABRY_RK_MIN_FACTOR 0.2
 #define DABRY_RK_MAX_FACTOR 10.0
@@ -185,6 +189,7 @@ DABRY_HD bool rk_step(RkState<N, KS>& S, const Rhs& rhs, double t_bound, double 
             scale[i] = atol + dmax(fabs(S.y[i]), fabs(y_new[i])) * rtol;
         }
         const double error_norm = rms_norm_scaled<N>(err, scale);
+        DABRY_TRACE_RK_ATTEMPT(N, t, h, error_norm);
         if (error_norm < 1.) {
             // The next step starts from min(h_abs * factor, max_step) (rk.py:121-126), so the power is only needed
             // when h_abs * factor can land below max_step.  factor >= r  <=>  error_norm <= (0.9 / r)^5; the test

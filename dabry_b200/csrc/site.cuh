@@ -152,6 +152,7 @@ struct ConstrRhs {
 };
 
 struct FreeEvents {
+    static constexpr bool kBothDirections = false;  // misc.py:34-43: every event of the solver has direction -1
     const ProblemDev& P;
     const SiteStore& S;
     int site;
@@ -182,6 +183,7 @@ DABRY_HD void arrival_note(const ProblemDev& P, const SiteStore& S, int s, int k
 }
 
 struct NoEvents {
+    static constexpr bool kBothDirections = false;
     DABRY_HD int count() const { return 0; }
     DABRY_HD bool terminal(int) const { return false; }
     DABRY_HD double value(int, double, const double*) const { return 0.; }
@@ -190,6 +192,7 @@ struct NoEvents {
 
 template <int FK>
 struct QuitEvent {
+    static constexpr bool kBothDirections = false;
     const ProblemDev& P;
     int obstacle;
     bool fired;
@@ -262,6 +265,9 @@ DABRY_HD void site_free_arc(const ProblemDev& P, const SiteStore& S, int s, int 
         if (site_in_obs_at(S, s, idx0)) return;
         carry.started = 0;
         ++n_calls;
+        // Trajectory.__add__ (trajectory.py:136-137): the events of a later arc replace those of the arcs before it, so
+        // events['target'] of a site integrated sub-frame by sub-frame (Trimming) holds the roots of its LAST free arc
+        S.n_target_events[s] = 0;
     }
     const int n = index_t - idx0 + 1;
     const Sample y0s = S.xp[S.at(s, idx0)];
@@ -381,6 +387,83 @@ DABRY_HD void site_obstacle_arcs(const ProblemDev& P, const SiteStore& S, int s,
         S.n_samples[s] += r3.n_emitted;
         if (qev.fired) S.closure[s] = CLOSURE_IMPOSSIBLE_OBS_TRACKING;
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// NavigationProblem.auto_time_upper_bound (problem.py:193-239): two feedback flights from x_init, each integrated by
+// solve_ivp (RK45, default tolerances, no step limit) until the target disc is entered -
+//   mode 0: GSTargetFB (feedback.py:58-89)  - ground velocity aimed at the target, full airspeed;
+//   mode 1: HTargetFB (feedback.py:92-130)  - heading aimed at the target, a UNIT control (not scaled by srf, as written).
+// The result is the root of the terminal target event, +inf when the flight runs out of time (rel_timeout).
+#define DABRY_EARTH_RADIUS 6378137.  // misc.py:183
+
+template <int FK>
+struct FeedbackRhs {
+    const ProblemDev& P;
+    int mode;
+    DABRY_HD void operator()(double t, const double* x, double* dx) const {
+        double e0, e1;
+        if (P.coords == COORDS_GCS) {  // chord to the target in the local east / north frame (feedback.py:69-79, 114-123)
+            double sl, cl, sp, cp, slt, clt, spt, cpt;
+            sincos(x[0], &sl, &cl);
+            sincos(x[1], &sp, &cp);
+            sincos(P.x_target[0], &slt, &clt);
+            sincos(P.x_target[1], &spt, &cpt);
+            const double d0 = DABRY_EARTH_RADIUS * (clt * cpt) - DABRY_EARTH_RADIUS * (cl * cp);
+            const double d1 = DABRY_EARTH_RADIUS * (slt * cpt) - DABRY_EARTH_RADIUS * (sl * cp);
+            const double d2 = DABRY_EARTH_RADIUS * spt - DABRY_EARTH_RADIUS * sp;
+            e0 = (d0 * -sl + d1 * cl) + d2 * 0.;
+            e1 = (d0 * (-sp * cl) + d1 * (-sp * sl)) + d2 * cp;
+        } else {
+            e0 = P.x_target[0] - x[0];
+            e1 = P.x_target[1] - x[1];
+        }
+        const double en = sqrt(e0 * e0 + e1 * e1);
+        Flow f;
+        field_eval<FK, false>(P.field, t, x[0], x[1], f);
+        double u0 = 0., u1 = 0.;
+        if (!(en <= 1e-8)) {  // np.isclose(norm, 0)
+            if (mode == 0) {
+                directional_control(f.w0, f.w1, e0, e1, P.srf, u0, u1);
+            } else {
+                const double ang = atan2(e1 / en, e0 / en);
+                sincos(ang, &u1, &u0);
+            }
+        }
+        if (P.coords == COORDS_GCS) {
+            dx[0] = (1. / cos(x[1])) * (u0 + f.w0);
+            dx[1] = u1 + f.w1;
+        } else {
+            dx[0] = u0 + f.w0;
+            dx[1] = u1 + f.w1;
+        }
+    }
+};
+
+struct TargetReached {  // event_target of apply_feedback (problem.py:209-212): terminal, no direction attribute = both
+    static constexpr bool kBothDirections = true;
+    const ProblemDev& P;
+    DABRY_HD int count() const { return 1; }
+    DABRY_HD bool terminal(int) const { return true; }
+    DABRY_HD double value(int, double, const double* x) const { return event_value(P, 0, x[0], x[1]); }
+    DABRY_HD void record(int, double) {}
+};
+
+struct NoSink {
+    DABRY_HD void emit(int, double, const double*) {}
+};
+
+template <int FK>
+DABRY_HD double feedback_flight_time(const ProblemDev& P, int mode, double x0, double x1, double t_start, double t_end,
+                                     unsigned& n_attempts) {
+    FeedbackRhs<FK> rhs{P, mode};
+    TargetReached ev{P};
+    NoSink sink;
+    const EvalGrid none = make_eval_grid(t_start, t_end, 0, 0);  // t_eval only samples: it does not steer the steps
+    IvpResult<2> res;
+    const double y0[2] = {x0, x1};
+    solve_ivp<2, METHOD_DOPRI5>(rhs, ev, sink, t_start, t_end, y0, none, INFINITY, P.rtol, P.atol, res, n_attempts);
+    return res.status == IVP_TERMINATED ? res.t_term : INFINITY;
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -181,8 +181,10 @@ class DiscreteFF(FlowField):
         self.coords = coords
         # (hi - lo) / (n - 1) per axis (flowfield.py:198-199)
         self.spacings = (bounds[:, 1] - bounds[:, 0]) / (np.array(values.shape[:-1]) - np.ones(values.ndim - 1))
-        self.grad_values = grad_values
+        self._grad_values = None
         self._grad_is_default = False
+        self._grad_fingerprint = None
+        self.grad_values = grad_values
         if not force_no_diff and self.grad_values is None:
             self.compute_derivatives()
         if values.ndim == 3:
@@ -193,6 +195,29 @@ class DiscreteFF(FlowField):
             self.d_value = self._d_value_unsteady
             self.t_start = bounds[0, 0]
             self.t_end = bounds[0, 1]
+
+    @property
+    def grad_values(self):
+        return self._grad_values
+
+    @grad_values.setter
+    def grad_values(self, value):
+        # a caller-supplied Jacobian is uploaded as it is; only the central differences of compute_derivatives are
+        # recomputed on the device instead of being shipped (dabry_b200/_lowering.py)
+        self._grad_values = value
+        self._grad_is_default = False
+        self._grad_fingerprint = None
+
+    @staticmethod
+    def _fingerprint(a):
+        flat = a.reshape(-1)
+        return hash(flat[::max(1, flat.shape[0] // 4096)].tobytes())
+
+    def grad_is_device_default(self):
+        """True when `grad_values` is still exactly what `compute_derivatives` produced (same array, not edited in
+        place as far as a strided fingerprint of 4 096 entries can tell): the device then differentiates by itself."""
+        return bool(self._grad_is_default and self._grad_values is not None
+                    and self._grad_fingerprint == self._fingerprint(self._grad_values))
 
     @property
     def times(self):
@@ -211,7 +236,7 @@ class DiscreteFF(FlowField):
         if not self.values.flags['WRITEABLE']:
             self.values = self.values.copy()
         pins = [nat.PinnedArray(self.values)]
-        if self.grad_values is not None and not self._grad_is_default:
+        if self.grad_values is not None and not self.grad_is_device_default():
             self.grad_values = np.array(self.grad_values, dtype=np.float64, order='C', copy=None)
             pins.append(nat.PinnedArray(self.grad_values))
         self._pins = pins
@@ -324,8 +349,9 @@ class DiscreteFF(FlowField):
         for a, b in ((0, 1), (-1, -2)):
             for c, d in ((0, 1), (-1, -2)):
                 g[..., a, c, :, :] = g[..., b, d, :, :]
-        self.grad_values = g
+        self._grad_values = g
         self._grad_is_default = True
+        self._grad_fingerprint = self._fingerprint(g)
 
     def dualize(self):
         ff = DiscreteFF.from_ff(-1. * self, self.bounds, self.values.shape[1], self.values.shape[2])

@@ -160,7 +160,10 @@ class NavigationProblem:
     def in_obs(self, state):
         return [obs for obs in self.obstacles if obs.value(state) < 0.]
 
-    # ---- time-horizon heuristics (host, one-off) ---------------------------------------------
+    # ---- time-horizon heuristics ------------------------------------------------------------
+    # The two arrival times that fix `total_duration` (and with it the time grid of a solve) come from the device:
+    # dabry_time_upper_bound integrates both feedback flights with the RK45 / event machinery of the extremals.  The
+    # host `apply_feedback` below only serves callers that want the whole feedback TRAJECTORY (display); no solver uses it.
     def apply_feedback(self, fb: Feedback, rel_timeout=10, n_time=1000) -> Trajectory:
         """Integrate the closed loop x' = f(t, x, fb(t, x)) until the target disc is entered (problem.py:193-214)."""
         t0 = self.model.ff.t_start
@@ -176,8 +179,16 @@ class NavigationProblem:
                               t_eval=times, events=[event_target])
         return Trajectory(res.t, res.y.transpose(), self.model.coords, events={'target': res.t_events[0]})
 
-    def auto_time_upper_bound(self):
-        return min(self.time_orthodromic(), self.time_htarget())
+    def auto_time_upper_bound(self, device=0):
+        return min(self._feedback_times(device))
+
+    def _feedback_times(self, device=0):
+        """(time_orthodromic, time_htarget) from the device, once per problem."""
+        cached = getattr(self, '_feedback_times_cache', None)
+        if cached is None:
+            from dabry_b200 import _lowering
+            cached = self._feedback_times_cache = _lowering.time_upper_bound(self, device=device)
+        return cached
 
     def orthodromic(self):
         return self.apply_feedback(GSTargetFB(self.model.ff, self.srf_max, self.x_target))
@@ -191,10 +202,10 @@ class NavigationProblem:
         return hits[0] if hits.size > 0 else np.inf
 
     def time_orthodromic(self):
-        return self._arrival_time(self.orthodromic())
+        return self._feedback_times()[0]
 
     def time_htarget(self):
-        return self._arrival_time(self.htarget())
+        return self._feedback_times()[1]
 
     # ---- non-dimensionalisation ------------------------------------------------------------------------------
     def rescale(self):

@@ -286,7 +286,7 @@ class SolverEF(ABC):
         self.pb = pb
         if total_duration is None:
             # 1.1 x the faster of the two feedback heuristics; 2 L / v when neither reaches the target (:302-309)
-            self.total_duration = 1.1 * self.pb.auto_time_upper_bound()
+            self.total_duration = 1.1 * self.pb.auto_time_upper_bound(device)
             if self.total_duration == np.inf:
                 self.total_duration = 2 * self.pb.length_reference / self.pb.srf_max
         else:

@@ -271,8 +271,8 @@ int dabry_get_cost_map_device(dabry_solver* h, int32_t full, double* d_out);
 int dabry_set_cost_map_device(dabry_solver* h, const double* d_map);
 
 /* ---- in-library collectives ------------------------------------------------------------------ */
-/* One process per GPU.  The ring of roots is sharded by theta_0 through dabry_config (root_offset / root_count /
- * shard_block / shard_world), the flow grid is replicated, and the library itself carries the three exchanges of the
+/* One process per GPU.  The ring of roots is sharded by theta_0 through the dabry_config fields root_offset, root_count,
+ * shard_block and shard_world, the flow grid is replicated, and the library itself carries the three exchanges of the
  * reference's loops over NCCL, enqueued on the solver's stream with no host round trip:
  *   - ring boundary (solver_ef.py:468-469): ncclSend / ncclRecv of one packet per local block inside one
  *     ncclGroupStart / ncclGroupEnd, after the roots are integrated (Trimming: every sub-frame);
@@ -298,6 +298,15 @@ int dabry_solve_sharded(dabry_solver* h, int32_t variant, const double* costates
 /* Global optimum after dabry_solve_sharded: arrival cost (NaN: none), the rank that holds the optimal extremal (lowest
  * rank among equals, -1: none) and the RK step attempts of all ranks. */
 int dabry_get_global_solution(dabry_solver* h, double* cost, int32_t* owner_rank, uint64_t* total_rk_steps);
+
+/* ---- time horizon --------------------------------------------------------------------- */
+/* NavigationProblem.auto_time_upper_bound (problem.py:193-239, feedback.py:58-130): the two feedback flights from x_init
+ * - ground velocity aimed at the target (GSTargetFB) and heading aimed at the target (HTargetFB, a unit control as
+ * written) - integrated on the device by the same RK45 / event root finder as the extremals (scipy defaults, no step
+ * limit, terminal target event of either direction) over [t_start, t_end] = [ff.t_start, ff.t_start + 10 L / srf].
+ * out[0] = time_orthodromic, out[1] = time_htarget; +inf when the target disc is not reached.  Uses the handle's flow
+ * field, coords, srf, x_target, target_radius, rtol and atol. */
+int dabry_time_upper_bound(dabry_solver* h, const double x_init[2], double t_start, double t_end, double out[2]);
 
 /* ---- evaluation hooks used by the parity tests ---------------------------------------------------------- */
 /* SolverEF.dyn_augsys(t, y) (solver_ef.py:355-359) for n points: t [n], y [n][4] -> dy [n][4]. */

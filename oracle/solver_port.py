@@ -152,7 +152,12 @@ class Port:
                  open_window=False, external_cost_maps=None):
         self.pb = pb
         if total_duration is None:
-            total_duration = 1.1 * pb.auto_time_upper_bound()
+            # problem.py:216-239 through the problem's own host feedback flights (scipy), never through the product's
+            # device routine
+            def arrival(traj):
+                hits = traj.events['target']
+                return hits[0] if hits.size > 0 else np.inf
+            total_duration = 1.1 * min(arrival(pb.orthodromic()), arrival(pb.htarget()))
             if total_duration == np.inf:
                 total_duration = 2 * pb.length_reference / pb.srf_max
         self.total_duration = total_duration

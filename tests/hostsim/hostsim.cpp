@@ -30,6 +30,16 @@ static FILE* hostsim_trace_file() {
         if (FILE* tf_ = hostsim_trace_file()) { fprintf(tf_, "%d %u\n", (int) (site), (unsigned) (attempts)); fflush(tf_); } \
     } while (0)
 
+// DABRY_HOSTSIM_TRACE_RK=<file>: one "n t h error_norm" line per RK step attempt (accept / reject analysis)
+static FILE* hostsim_rk_trace_file() {
+    static FILE* f = getenv("DABRY_HOSTSIM_TRACE_RK") ? fopen(getenv("DABRY_HOSTSIM_TRACE_RK"), "w") : nullptr;
+    return f;
+}
+#define DABRY_TRACE_RK_ATTEMPT(n, t, h, error_norm)                                                    \
+    do {                                                                                               \
+        if (FILE* tf_ = hostsim_rk_trace_file()) fprintf(tf_, "%d %.17g %.17g %.17g\n", (int) (n), (double) (t), (double) (h), (double) (error_norm)); \
+    } while (0)
+
 #include "../../dabry_b200/csrc/engine.cuh"
 
 namespace dabry {

@@ -58,12 +58,20 @@ def golden_keys(kind=None):
     return [k for k in keys if kind is None or k.endswith('_' + kind)]
 
 
-def solve_case(key):
-    from cases import CASES, build_problem, run_solver
+def solve_case(key, horizon=None):
+    """horizon: `total_duration` to pass explicitly (the golden record's, bit for bit) instead of letting the solver
+    derive it from the feedback flights - step counts are compared exactly, and one more step is attempted per arc when
+    the horizon moves by an ulp (100 steps of 0.01 T either reach T or fall one ulp short of it)."""
+    from cases import CASES, SOLVERS, build_problem, run_solver, solver_args
     api = package_api()
     case = CASES[key]
     pb = build_problem(case, api)
-    return case, run_solver(case, pb, api)
+    if horizon is None or case.solver == 'S':
+        return case, run_solver(case, pb, api)
+    args, kwargs = solver_args(case, pb)
+    solver = getattr(api, SOLVERS[case.solver])(pb, float(horizon), **kwargs)
+    solver.solve()
+    return case, solver
 
 
 def scaled_diff(a, b):

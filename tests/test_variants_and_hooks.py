@@ -9,6 +9,8 @@
 
 Every test body runs twice: on the GPU through libdabry_b200.so (`-m gpu`) and on tests/hostsim (CPU tier).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -104,9 +106,10 @@ def rk4_fixed_matches_oracle():
     for name in ('gyre', 'obstacle', 'spherical_geodesic'):
         pb = NavigationProblem.from_name(name).rescale()
         kw = dict(max_depth=3, n_costate_sectors=24, n_time=101)
-        solver = SolverEFResampling(pb, integrator='rk4', **kw)
-        solver.solve()
         port = Port(pb, integrator='rk4', **kw).run_resampling()
+        # same horizon bit for bit (the solver would derive its own on the device): step counts are compared exactly
+        solver = SolverEFResampling(pb, port.total_duration, integrator='rk4', **kw)
+        solver.solve()
         mine, ref = solver_record(solver, full=True), pu.port_record(port)
         pu.compare_sites_record(mine, ref)
         pu.compare_full_trajectories(mine, ref)
@@ -529,6 +532,96 @@ def test_legacy_rff_and_traj_exporters(hostsim, tmp_path, monkeypatch):
     assert np.array_equal(g['data'], site0.traj.states) and np.array_equal(g['ts'], site0.traj.times)
     assert np.array_equal(g['adjoints'], site0.traj.costates, equal_nan=True) and g['controls'].shape == (len(site0.traj),)
     s.close()
+
+
+def time_upper_bound_on_device():
+    """`auto_time_upper_bound` (problem.py:193-239) on the device against scipy on the host feedback
+    flights, for the 11 CI cases of the reference.  These flights run without a step limit (error-controlled steps of
+    rtol = 1e-3), so their arrival time is as sharp as the integrator lets rounding be: the conditioning of each flight is
+    measured on scipy itself (the same flight with the control moved by <= 1 ulp per call), and the device must agree to
+    1e-12 or to 100 x that spread.  The bound that matters - the smaller of the two, which fixes `total_duration` and the
+    time grid - must also match the golden record of the unmodified reference to 1e-10."""
+    from cases import CI_CASES, TIME_BOUND
+    from dabry_b200.feedback import GSTargetFB, HTargetFB
+    from dabry_b200.problem import NavigationProblem
+
+    class Nudged:
+        def __init__(self, fb, seed):
+            self.fb, self.rng = fb, np.random.default_rng(seed)
+
+        def __call__(self, t, x):
+            v = np.asarray(self.fb(t, x), dtype=float)
+            k = self.rng.integers(-1, 2, size=v.shape)
+            return np.where(k > 0, np.nextafter(v, np.inf), np.where(k < 0, np.nextafter(v, -np.inf), v))
+
+    arrival = NavigationProblem._arrival_time
+    for name in CI_CASES:
+        pb = NavigationProblem.from_name(name).rescale()
+        dev = pb._feedback_times()
+        laws = (GSTargetFB(pb.model.ff, pb.srf_max, pb.x_target), HTargetFB(pb.x_target, pb.model.coords))
+        host = tuple(arrival(pb.apply_feedback(fb)) for fb in laws)
+        for a, b, fb in zip(dev, host, laws):
+            if np.isinf(b):
+                assert np.isinf(a), (name, dev, host)
+                continue
+            spread = max(abs(arrival(pb.apply_feedback(Nudged(fb, seed))) - b) for seed in (1, 2, 3))
+            assert abs(a - b) <= max(1e-12 * max(1., abs(b)), 100. * spread), (name, dev, host, spread)
+        if name not in TIME_BOUND:
+            g = pu.golden(name + '_R')
+            total = 1.1 * min(dev)
+            if total == np.inf:
+                total = 2 * pb.length_reference / pb.srf_max
+            assert abs(total - float(g['total_duration'])) <= 1e-10 * max(1., float(g['total_duration'])), name
+
+
+test_time_upper_bound_on_device_hostsim, test_time_upper_bound_on_device_gpu = _both(time_upper_bound_on_device)
+
+
+def exporters_against_oracle():
+    """SURVEY 8(f) rank 3 against the ORACLE, not against itself: the legacy rff product (`save_rff`, data[k] = V - ts[k]
+    with V the device cost map of the whole front) equals what the oracle's restatement of cost_map_triangle
+    (solver_ef.py:860-889) gives for its own front, cell by cell in the interior of the map (border cells depend on
+    extremals sliding on the frame), and the one-file front bundle (`save_front_bundle`) holds the oracle's
+    trajectories."""
+    import tempfile
+    from dabry_b200.problem import NavigationProblem
+    from dabry_b200.solver_ef import SolverEFResampling
+    from solver_port import Port
+    name, depth = 'obstacle', 5
+    pb = NavigationProblem.from_name(name).rescale()
+    tmp = tempfile.mkdtemp(prefix='dabry_export_')
+    pb.io.set_case_dir(os.path.join(tmp, 'case'))
+    s = SolverEFResampling(pb, max_depth=depth)
+    s.solve()
+    port = Port(pb, max_depth=depth)
+    port.run_resampling()
+    ref_map = port.cost_map(port.sites.values(), 0, port.n_time - 1)
+    with np.load(s.save_rff(fmt='npz')) as f:
+        data, ts, grid = f['data'], f['ts'], f['grid']
+    assert np.array_equal(ts, port.times)
+    value = data[0] + ts[0] - s.t_init  # data[k] = V + t_init - ts[k]
+    inner = (slice(1, -1), slice(1, -1))
+    assert np.array_equal(np.isfinite(value[inner]), np.isfinite(ref_map[inner]))
+    fin = np.isfinite(ref_map[inner])
+    assert fin.sum() > 1000
+    assert np.max(np.abs(value[inner][fin] - ref_map[inner][fin])) <= 1e-9
+    for k in (0, 37, 99):
+        assert np.array_equal(data[k], data[0] + ts[0] - ts[k])
+    gx = np.linspace(pb.bl[0], pb.tr[0], 100)
+    assert np.array_equal(grid[:, 0, 0], gx)
+    # the bundle: padded trajectories + records of every site, in insertion order
+    s.save_front_bundle('front')
+    with np.load(os.path.join(pb.io.trajs_dir, 'front.npz')) as f:
+        names, states, records, times_grid = list(f['names']), f['states'], f['records'], f['times_grid']
+    assert names == [x.name for x in port.sites.values()] and np.array_equal(times_grid, port.times)
+    for i, site in enumerate(port.sites.values()):
+        k0, n = site.index_t_init, len(site.t)
+        assert records['index_t_init'][i] == k0 and records['n_samples'][i] == n
+        assert np.max(np.abs(states[i, k0:k0 + n] - np.array(site.x))) <= 1e-9
+    s.close()
+
+
+test_exporters_against_oracle_hostsim, test_exporters_against_oracle_gpu = _both(exporters_against_oracle)
 
 
 def test_root_fan_matches_numpy_and_shards():
