@@ -93,6 +93,12 @@ def apply_penalty(handle, penalty):
     pen.scaler, pen.dx = d['scaler'], d['dx']
     for k, v in enumerate(d['params']):
         pen.p[k] = v
+    grid = d.get('grid')
+    if grid is not None:  # DiscretePenalty: a second gathered grid (data, ts, xs, ys)
+        data, ts, xs, ys = (nat.f64(a) for a in grid)
+        handle.call('dabry_set_penalty_grid', C.byref(pen), nat.dptr(data), nat.dptr(ts), nat.dptr(xs), nat.dptr(ys),
+                    data.shape[0], data.shape[1], data.shape[2])
+        return
     handle.call('dabry_set_penalty', C.byref(pen))
 
 

@@ -53,7 +53,7 @@ class Leaf(C.Structure):
 
 class Obstacle(C.Structure):
     _fields_ = [('kind', C.c_int32), ('pad_', C.c_int32), ('scale_length', C.c_double), ('bl', C.c_double * 2),
-                ('p', C.c_double * 6)]
+                ('p', C.c_double * 8)]
 
 
 class Penalty(C.Structure):
@@ -99,6 +99,8 @@ SIGNATURES = {
     'dabry_set_flow_program': (C.c_int, [_H, C.POINTER(Leaf), C.c_int32, c_double_p, C.c_int64, C.POINTER(Wrapper)]),
     'dabry_set_obstacles': (C.c_int, [_H, C.POINTER(Obstacle), C.c_int32]),
     'dabry_set_penalty': (C.c_int, [_H, C.POINTER(Penalty)]),
+    'dabry_set_penalty_grid': (C.c_int, [_H, C.POINTER(Penalty), c_double_p, c_double_p, c_double_p, c_double_p, C.c_int32,
+                                         C.c_int32, C.c_int32]),
     'dabry_setup': (C.c_int, [_H, C.c_int32, c_double_p]),
     'dabry_step': (C.c_int, [_H]),
     'dabry_step_integrate': (C.c_int, [_H]),

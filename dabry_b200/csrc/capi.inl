@@ -134,6 +134,13 @@ int dabry_set_penalty(dabry_solver* h, const dabry_penalty* pen) {
     return E.set_penalty(pen);
 }
 
+int dabry_set_penalty_grid(dabry_solver* h, const dabry_penalty* pen, const double* data, const double* ts,
+                           const double* xs, const double* ys, int32_t nt, int32_t nx, int32_t ny) {
+    DABRY_GUARD(h);
+    if (!pen) return E.fail(DABRY_ERR_INVALID, "penalty missing");
+    return E.set_penalty_grid(pen, data, ts, xs, ys, nt, nx, ny);
+}
+
 int dabry_setup(dabry_solver* h, int32_t variant, const double* costates) {
     DABRY_GUARD(h);
     return E.setup(variant, costates);

@@ -644,6 +644,8 @@ public:
         free_store(S);
         be.free(d_times);
         be.free(d_tables);
+        be.free(d_pen_data);
+        be.free(d_pen_axes);
         be.free(d_grid);
         be.free(d_request);
         be.free(d_offset);
@@ -851,8 +853,31 @@ public:
     }
 
     int set_penalty(const dabry_penalty* pen) {
+        if (pen->kind == PEN_GRID) return fail(DABRY_ERR_INVALID, "a gridded penalty is set with dabry_set_penalty_grid");
         memcpy(&P.penalty, pen, sizeof(dabry_penalty));
         return DABRY_OK;
+    }
+
+    // DiscretePenalty (penalty.py:96-134): data[nt][nx][ny] on the axes ts / xs / ys, through the WrapperPen parameters
+    // of `pen` (kind is set here)
+    int set_penalty_grid(const dabry_penalty* pen, const double* data, const double* ts, const double* xs,
+                         const double* ys, int nt, int nx, int ny) {
+        if (!data || !ts || !xs || !ys || nt < 2 || nx < 2 || ny < 2)
+            return fail(DABRY_ERR_INVALID, "penalty grid: need data and three axes of at least two nodes");
+        be.free(d_pen_data);
+        be.free(d_pen_axes);
+        const int64_t n = (int64_t) nt * nx * ny;
+        d_pen_data = (double*) be.alloc(sizeof(double) * n);
+        d_pen_axes = (double*) be.alloc(sizeof(double) * (nt + nx + ny));
+        if (!d_pen_data || !d_pen_axes) return fail(DABRY_ERR_CAPACITY, "out of device memory (penalty grid)");
+        be.upload(d_pen_data, data, sizeof(double) * n);
+        be.upload(d_pen_axes, ts, sizeof(double) * nt);
+        be.upload(d_pen_axes + nt, xs, sizeof(double) * nx);
+        be.upload(d_pen_axes + nt + nx, ys, sizeof(double) * ny);
+        memcpy(&P.penalty, pen, sizeof(dabry_penalty));
+        P.penalty.kind = PEN_GRID;
+        P.penalty_grid = PenaltyGrid{d_pen_data, d_pen_axes, d_pen_axes + nt, d_pen_axes + nt + nx, nt, nx, ny, 0};
+        return check();
     }
 
     // ---- solve ----
@@ -1371,6 +1396,8 @@ private:
     std::vector<double> times_h;
     double* d_times = nullptr;
     double* d_tables = nullptr;
+    double* d_pen_data = nullptr;  // DiscretePenalty samples and axes
+    double* d_pen_axes = nullptr;
     double* d_grid = nullptr;
     int32_t* d_request = nullptr;
     int32_t* d_offset = nullptr;

@@ -127,7 +127,7 @@ DABRY_HD_NOINLINE EventStep<N> event_step(const Dense<N> D, Events& events, Sink
 // Events concept:  int count() const;  bool terminal(int e) const;  double value(int e, double t, const double* y) const;
 //                  void record(int e, double t_root);
 // Sink concept:    void emit(int j, double t, const double* y);     j indexes the un-sliced linspace
-template <int N, int METHOD, class KS = KRegisters<N>, class Rhs, class Events, class Sink>
+template <int N, int METHOD, class KS = KRegisters<N>, bool DEFER = false, class Rhs, class Events, class Sink>
 DABRY_HD void solve_ivp(const Rhs& rhs, Events& events, Sink& sink, double t0, double tf, const double* y0,
                         const EvalGrid& grid, double max_step, double rtol, double atol, IvpResult<N>& res,
                         unsigned& n_attempts, IvpCarry<N>* carry = nullptr, int step_budget = 0, KS kstore = KS(),
@@ -187,13 +187,14 @@ DABRY_HD void solve_ivp(const Rhs& rhs, Events& events, Sink& sink, double t0, d
             S.t_old = S.t;
             finished = true;
         } else {
-            const bool ok = METHOD == METHOD_RK4 ? rk4_step<N>(S, rhs, tf, max_step, n_attempts)
-                                                 : rk_step<N>(S, rhs, tf, max_step, rtol, atol, n_attempts);
-            if (!ok) {
+            const int ok = METHOD == METHOD_RK4 ? (int) rk4_step<N>(S, rhs, tf, max_step, n_attempts)
+                                                : rk_step<N, DEFER>(S, rhs, tf, max_step, rtol, atol, n_attempts);
+            if (ok == 0) {
                 res.status = IVP_FAILED;
                 res.n_emitted = n_emitted;
                 return;
             }
+            if (DEFER && ok == 2) continue;  // rejected: the same step again in the next round, nothing else happened
             if (S.t - tf >= 0.) finished = true;
         }
         const double t_old = S.t_old;

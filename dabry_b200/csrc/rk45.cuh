@@ -63,6 +63,7 @@ struct RkState {
     double t, t_old, h_abs;
     double y[N];
     KS K;
+    bool retry = false;  // DEFER builds: the last attempt was rejected, the next call of rk_step repeats the step
 };
 
 template <int N>
@@ -124,24 +125,31 @@ DABRY_HD bool rk_init(RkState<N, KS>& S, const Rhs& rhs, double t0, const double
     return true;
 }
 
-// One accepted step of RungeKutta._step_impl (rk.py:111-176).  Returns false on TOO_SMALL_STEP.
+// One accepted step of RungeKutta._step_impl (rk.py:111-176).  Returns 1, or 0 on TOO_SMALL_STEP.
 // n_attempts is incremented once per attempted step (accepted or rejected): the metric's unit.
-template <int N, class KS, class Rhs>
-DABRY_HD bool rk_step(RkState<N, KS>& S, const Rhs& rhs, double t_bound, double max_step, double rtol, double atol,
-                      unsigned& n_attempts) {
+// DEFER: a rejected attempt returns 2 instead of looping (scipy's `while not step_accepted`), and the caller calls again;
+// per-extremal arithmetic is identical, but the lanes of a warp whose attempt was accepted do not wait for the retry of
+// the ones that rejected - those repeat their step in the warp's next round.
+template <int N, bool DEFER = false, class KS, class Rhs>
+DABRY_HD int rk_step(RkState<N, KS>& S, const Rhs& rhs, double t_bound, double max_step, double rtol, double atol,
+                     unsigned& n_attempts) {
     const double t = S.t;
     // min_step = 10 ulp(t) (rk.py:119) only matters when the step is within a few ulps of t: 10 ulp(t) <= 4.5e-15 |t|,
     // so any h_abs above 1e-12 (|t| + 1) is provably larger and nextafter is skipped
     double h_abs = S.h_abs;
     const double safe = 1e-12 * (fabs(t) + 1.);
-    if (h_abs > max_step) h_abs = max_step;
-    else if (!(h_abs > safe) && h_abs < 10. * ulp_above(t)) h_abs = 10. * ulp_above(t);
-    bool rejected = false;
+    bool rejected = DEFER && S.retry;
+    if (!rejected) {
+        if (h_abs > max_step) h_abs = max_step;
+        else if (!(h_abs > safe) && h_abs < 10. * ulp_above(t)) h_abs = 10. * ulp_above(t);
+    }
     double y_new[N];
+    if (!rejected) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) S.K[0][i] = S.K[6][i];  // FSAL: f(t, y) of the last accepted step
+        for (int i = 0; i < N; ++i) S.K[0][i] = S.K[6][i];  // FSAL: f(t, y) of the last accepted step
+    }
     for (;;) {
-        if (!(h_abs > safe) && h_abs < 10. * ulp_above(t)) return false;
+        if (!(h_abs > safe) && h_abs < 10. * ulp_above(t)) return 0;
         double t_new = t + h_abs;
         if (t_new - t_bound > 0.) t_new = t_bound;
         const double h = t_new - t;
@@ -213,6 +221,11 @@ DABRY_HD bool rk_step(RkState<N, KS>& S, const Rhs& rhs, double t_bound, double 
         }
         h_abs *= dmax(DABRY_RK_MIN_FACTOR, DABRY_RK_SAFETY * pow(error_norm, -0.2));
         rejected = true;
+        if (DEFER) {  // K[0] = f(t, y) and y are untouched: the next call repeats the step with the smaller h_abs
+            S.h_abs = h_abs;
+            S.retry = true;
+            return 2;
+        }
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) {
@@ -220,7 +233,8 @@ DABRY_HD bool rk_step(RkState<N, KS>& S, const Rhs& rhs, double t_bound, double 
         S.y[i] = y_new[i];
     }
     S.h_abs = h_abs;
-    return true;
+    if (DEFER) S.retry = false;
+    return 1;
 }
 
 // Quartic dense output of the last accepted step (rk.py:178-180, 715-737): Q = K^T P, P from rk.py:553-565.

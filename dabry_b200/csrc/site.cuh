@@ -19,6 +19,11 @@
 #ifndef DABRY_K_IN_SHARED
 #define DABRY_K_IN_SHARED 0
 #endif
+// 1: a lane whose step attempt is rejected repeats it in the warp's next round instead of inside scipy's inner loop
+// (rk45.cuh rk_step DEFER) - free arcs of the one-launch builds only
+#ifndef DABRY_DEFER_RETRY
+#define DABRY_DEFER_RETRY 0
+#endif
 #ifndef DABRY_FREE_ARC_THREADS
 #define DABRY_FREE_ARC_THREADS 128  // block size of the free-arc kernel (FreeArcPhase::kThreads)
 #endif
@@ -285,8 +290,9 @@ DABRY_HD void site_free_arc(const ProblemDev& P, const SiteStore& S, int s, int 
         CHUNKED ? &carry : nullptr, CHUNKED ? step_budget : 0, KShared<4, DABRY_FREE_ARC_THREADS>{k_tile + threadIdx.x},
         t_park);
 #else
-    solve_ivp<4, METHOD>(rhs, ev, sink, grid.at(0), grid.at(n - 1), y0, grid, P.max_step, P.rtol, P.atol, res, n_attempts,
-                         CHUNKED ? &carry : nullptr, CHUNKED ? step_budget : 0, KRegisters<4>(), t_park);
+    solve_ivp<4, METHOD, KRegisters<4>, (!CHUNKED && DABRY_DEFER_RETRY != 0)>(
+        rhs, ev, sink, grid.at(0), grid.at(n - 1), y0, grid, P.max_step, P.rtol, P.atol, res, n_attempts,
+        CHUNKED ? &carry : nullptr, CHUNKED ? step_budget : 0, KRegisters<4>(), t_park);
 #endif
     if (CHUNKED && res.status == IVP_DEFERRED) {  // nothing happened yet: a later window starts this arc afresh
         S.flags[s] |= SITE_DEFERRED;

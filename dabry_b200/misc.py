@@ -154,6 +154,30 @@ class Utils:
         return np.angle(np.cos(a) + 1j * np.sin(a))
 
     @staticmethod
+    def to_0_360(angle):
+        """Angle in degrees brought to [0, 360[ (misc.py:186-192)."""
+        return angle - 360. * math.floor(angle / 360.)
+
+    @staticmethod
+    def rectify(a, b):
+        """Two angles in degrees brought to [0, 720[ keeping their order (misc.py:200-211)."""
+        lo, hi = Utils.to_0_360(a), Utils.to_0_360(b)
+        return lo, hi + 360. if lo > hi else hi
+
+    @staticmethod
+    def angular_diff(a1, a2):
+        """Unsigned angle between two directions in radians (misc.py:223-235)."""
+        d = abs(Utils.ang_principal(a2) - Utils.ang_principal(a1))
+        return d if d <= np.pi else 2 * np.pi - d
+
+    @staticmethod
+    def in_lonlat_box(bl, tr, p):
+        """True when (lon, lat) = p in radians lies strictly inside the box [bl, tr] (misc.py:558-568)."""
+        lon_lo, lon_hi = Utils.rectify(Utils.RAD_TO_DEG * bl[0], Utils.RAD_TO_DEG * tr[0])
+        lon = Utils.to_0_360(Utils.RAD_TO_DEG * p[0])
+        return (lon_lo < lon < lon_hi or lon_lo < lon + 360 < lon_hi) and bl[1] < p[1] < tr[1]
+
+    @staticmethod
     def central_angle_cos(x1, x2):
         return math.sin(x1[1]) * math.sin(x2[1]) + math.cos(x1[1]) * math.cos(x2[1]) * math.cos(x2[0] - x1[0])
 

@@ -8,9 +8,9 @@ from typing import Union
 import numpy as np
 from numpy import ndarray
 
-from dabry_b200.misc import terminal
+from dabry_b200.misc import terminal, Utils
 
-OBS_CIRCLE, OBS_FRAME = 0, 1
+OBS_CIRCLE, OBS_FRAME, OBS_GREAT_CIRCLE = 0, 1, 2
 
 
 class Obstacle(ABC):
@@ -109,3 +109,47 @@ class FrameObs(Obstacle):
     def lower(self):
         return OBS_FRAME, 1., (0., 0.), (float(self.center[0]), float(self.center[1]),
                                           float(self.scaler[0, 0]), float(self.scaler[1, 1]))
+
+
+class GreatCircleObs(Obstacle):
+    """Half-space beyond the great circle through p1 and p2, optionally limited to a lon/lat zone [z1, z2]
+    (obstacle.py:131-172).  value = X(x) . dir with X the unit vector of (lon, lat) and dir = -(X1 x X2) / |X1 x X2|;
+    outside the zone the value is 1 and the gradient (1, 1), as written."""
+
+    def __init__(self, p1, p2, z1=None, z2=None, autobox=False):
+        def unit(p):
+            return np.array((np.cos(p[0]) * np.cos(p[1]), np.sin(p[0]) * np.cos(p[1]), np.sin(p[1])))
+
+        if autobox:
+            # as in the reference, the latitude extent is p1[1] - p2[0] (lat of p1 minus LON of p2, obstacle.py:151)
+            delta_lon = Utils.angular_diff(p1[0], p2[0])
+            delta_lat = p1[1] - p2[0]
+            self.z1 = np.array((min(p1[0] - delta_lon / 2., p2[0] - delta_lon / 2.),
+                                min(p1[1] - delta_lat / 2., p2[1] - delta_lat / 2.)))
+            self.z2 = np.array((max(p1[0] + delta_lon / 2., p2[0] + delta_lon / 2.),
+                                max(p1[1] + delta_lat / 2., p2[1] + delta_lat / 2.)))
+        else:
+            self.z1, self.z2 = z1, z2
+        self.dir_vect = -np.cross(unit(p1), unit(p2))
+        self.dir_vect /= np.linalg.norm(self.dir_vect)
+        super().__init__()
+
+    def _outside_zone(self, x):
+        return self.z1 is not None and not Utils.in_lonlat_box(self.z1, self.z2, x)
+
+    def value(self, x):
+        if self._outside_zone(x):
+            return 1.
+        return np.array((np.cos(x[0]) * np.cos(x[1]), np.sin(x[0]) * np.cos(x[1]), np.sin(x[1]))) @ self.dir_vect
+
+    def d_value(self, x):
+        if self._outside_zone(x):
+            return np.array((1., 1.))
+        d_lon = np.array((-np.sin(x[0]) * np.cos(x[1]), np.cos(x[0]) * np.cos(x[1]), 0))
+        d_lat = np.array((-np.cos(x[0]) * np.sin(x[1]), -np.sin(x[0]) * np.sin(x[1]), np.cos(x[1])))
+        return np.array((self.dir_vect @ d_lon, self.dir_vect @ d_lat))
+
+    def lower(self):
+        zone = (0., 0., 0., 0., 0.) if self.z1 is None else (float(self.z1[0]), float(self.z1[1]), float(self.z2[0]),
+                                                             float(self.z2[1]), 1.)
+        return OBS_GREAT_CIRCLE, 1., (0., 0.), tuple(float(v) for v in self.dir_vect) + zone

@@ -7,7 +7,7 @@ finite difference with step 1e-8 (penalty.py:39-44), which the device reproduces
 import numpy as np
 from numpy import ndarray
 
-PEN_NONE, PEN_CIRCLE = 0, 1
+PEN_NONE, PEN_CIRCLE, PEN_GRID = 0, 1, 2
 
 
 class Penalty:
@@ -97,8 +97,9 @@ class CirclePenalty(Penalty):
 
 
 class DiscretePenalty(Penalty):
-    """Penalty sampled on a (t, x, y) grid, linear interpolation, zero outside (penalty.py:96-134).  Host-side
-    only in this build: `lower()` raises."""
+    """Penalty sampled on a (t, x, y) grid, linear interpolation, zero outside (penalty.py:96-134).  On the device it is
+    a second gathered grid (`dabry_set_penalty_grid`): scipy's RegularGridInterpolator restated with numpy's roundings,
+    differentiated by the same central differences (dx = 1e-8)."""
 
     def __init__(self, *args):
         super().__init__()
@@ -116,3 +117,11 @@ class DiscretePenalty(Penalty):
         from scipy.interpolate import RegularGridInterpolator
         self.itp = RegularGridInterpolator((self.ts, self.grid[:, 0, 0].copy(), self.grid[0, :, 1].copy()), self.data,
                                            method='linear', bounds_error=False, fill_value=0.)
+
+    def lower(self):
+        if self.data is None:
+            raise TypeError('DiscretePenalty without data has no device implementation')
+        d = _identity_lowering(PEN_GRID, self._dx)
+        d['grid'] = (np.asarray(self.data, dtype=float), np.asarray(self.ts, dtype=float),
+                     np.asarray(self.grid[:, 0, 0], dtype=float), np.asarray(self.grid[0, :, 1], dtype=float))
+        return d

@@ -28,6 +28,7 @@ class SyntheticCase:
     total_duration: Optional[float] = None
     circle_obstacles: list = field(default_factory=list)  # [(center(2,), radius)]
     circle_penalty: Optional[tuple] = None  # (center(2,), radius, amplitude)
+    discrete_penalty: Optional[tuple] = None  # (data (nt, nx, ny), ts (nt,), grid (nx, ny, 2)) of a DiscretePenalty
     name: str = 'synthetic'
 
 
@@ -117,3 +118,22 @@ def regional_constrained(nt: int = 17, nx: int = 181, ny: int = 101, seed: int =
     pen = (x_init + 0.3 * chord - 0.05 * np.linalg.norm(chord) * normal, 0.1 * ext, 1.)
     return SyntheticCase(values, bounds, 'gcs', x_init, x_target, SRF_AIRSPEED, bl, tr,
                          circle_obstacles=obs, circle_penalty=pen, name='regional_constrained')
+
+
+def regional_discrete_penalty(nt: int = 9, nx: int = 91, ny: int = 51, seed: int = 20231021) -> SyntheticCase:
+    """Config 5 variant for SURVEY 8(f) rank 4: the regional case with its circular obstacle, the penalty given as a
+    `DiscretePenalty` - a pulsating Gaussian bump sampled on a coarse (7, 31, 21) grid over the box and the 48 h."""
+    sc = regional_constrained(nt, nx, ny, seed)
+    ts = np.linspace(0., 48 * 3600., 7)
+    xs = np.linspace(sc.bl[0], sc.tr[0], 31)
+    ys = np.linspace(sc.bl[1], sc.tr[1], 21)
+    chord = sc.x_target - sc.x_init
+    normal = np.array((-chord[1], chord[0])) / np.linalg.norm(chord)
+    c = sc.x_init + 0.3 * chord - 0.05 * np.linalg.norm(chord) * normal
+    gx, gy = np.meshgrid(xs, ys, indexing='ij')
+    bump = 4e-3 * np.exp(-((gx - c[0]) ** 2 + (gy - c[1]) ** 2) / (2 * 0.07 ** 2))
+    data = bump[None, :, :] * (1. + 0.3 * np.sin(2 * np.pi * ts / (24 * 3600.)))[:, None, None]
+    sc.circle_penalty = None
+    sc.discrete_penalty = (data, ts, np.stack((gx, gy), -1))
+    sc.name = 'regional_discrete_penalty'
+    return sc

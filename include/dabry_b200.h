@@ -104,16 +104,17 @@ typedef struct dabry_leaf {
     double p[8];
 } dabry_leaf;
 
-enum dabry_obstacle_kind { DABRY_OBS_CIRCLE = 0, DABRY_OBS_FRAME = 1 };   /* obstacle.py:84-99, 102-128 */
+enum dabry_obstacle_kind { DABRY_OBS_CIRCLE = 0, DABRY_OBS_FRAME = 1, DABRY_OBS_GREAT_CIRCLE = 2 }; /* obstacle.py:84-172 */
 
 typedef struct dabry_obstacle {
     int32_t kind;
     int32_t pad_;
     double scale_length, bl[2]; /* WrapperObs (obstacle.py:66-81); identity = 1, {0, 0} */
-    double p[6];                /* circle: center(2), radius**2 | frame: center(2), scaler diagonal(2) */
+    double p[8];                /* circle: center(2), radius**2 | frame: center(2), scaler diagonal(2) |
+                                   great circle: dir_vect(3), zone z1(2), z2(2), 1 if the zone is set else 0 */
 } dabry_obstacle;
 
-enum dabry_penalty_kind { DABRY_PEN_NONE = 0, DABRY_PEN_CIRCLE = 1 };    /* penalty.py:72-93 */
+enum dabry_penalty_kind { DABRY_PEN_NONE = 0, DABRY_PEN_CIRCLE = 1, DABRY_PEN_GRID = 2 }; /* penalty.py:72-134 */
 
 typedef struct dabry_penalty {
     int32_t kind;
@@ -201,6 +202,12 @@ int dabry_set_flow_program(dabry_solver* h, const dabry_leaf* leaves, int32_t n_
 /* pb.obstacles in order, the auto frame last (problem.py:100-104; solver_ef.py:322-334). */
 int dabry_set_obstacles(dabry_solver* h, const dabry_obstacle* obstacles, int32_t n);
 int dabry_set_penalty(dabry_solver* h, const dabry_penalty* penalty);
+/* DiscretePenalty (penalty.py:96-134): data [nt][nx][ny] sampled on the (not necessarily uniform) axes ts / xs / ys,
+ * interpolated like scipy's RegularGridInterpolator(method='linear', bounds_error=False, fill_value=0) and
+ * differentiated by central differences with penalty->dx like Penalty.d_value (penalty.py:39-44); `penalty` carries
+ * the WrapperPen parameters and dx (its kind and p[] are ignored).  The arrays are copied. */
+int dabry_set_penalty_grid(dabry_solver* h, const dabry_penalty* penalty, const double* data, const double* ts,
+                           const double* xs, const double* ys, int32_t nt, int32_t nx, int32_t ny);
 
 /* ---- solve --------------------------------------------------------------------------------------------- */
 /* SolverEFResampling.setup (solver_ef.py:462-470) / SolverEFTrimming.setup (778-782) / the fan of

@@ -42,12 +42,16 @@ CASES['era5_like_R'] = _case('era5_like_R', 'synthetic', 'R', gen='era5_like', g
                              solver_kwargs=dict(max_depth=6))
 CASES['regional_constrained_R'] = _case('regional_constrained_R', 'synthetic', 'R', gen='regional_constrained',
                                         gen_args=(9, 91, 51), solver_kwargs=dict(max_depth=6))
+CASES['regional_discrete_penalty_R'] = _case('regional_discrete_penalty_R', 'synthetic', 'R',
+                                            gen='regional_discrete_penalty', gen_args=(9, 91, 51),
+                                            solver_kwargs=dict(max_depth=6))
 CASES['regional_constrained_T'] = _case('regional_constrained_T', 'synthetic', 'T', gen='regional_constrained',
                                         gen_args=(9, 91, 51), solver_kwargs=dict(max_depth=8))
 
 
 def build_problem(case, api):
-    """``api`` needs: NavigationProblem, DiscreteFF, Coords, CircleObs, CirclePenalty."""
+    """``api`` needs: NavigationProblem, DiscreteFF, Coords, CircleObs, CirclePenalty (DiscretePenalty for the case that
+    uses one)."""
     if case.kind == 'catalog':
         return api.NavigationProblem.from_name(case.name).rescale()
     from dabry_b200 import synthetic
@@ -59,6 +63,8 @@ def build_problem(case, api):
     if sc.circle_penalty is not None:
         c, r, a = sc.circle_penalty
         penalty = api.CirclePenalty(np.array(c), float(r), float(a))
+    if getattr(sc, 'discrete_penalty', None) is not None:
+        penalty = api.DiscretePenalty(*sc.discrete_penalty)
     pb = api.NavigationProblem(ff, sc.x_init, sc.x_target, sc.srf, bl=sc.bl, tr=sc.tr,
                                obstacles=obstacles, penalty=penalty, name=sc.name)
     return pb.rescale()

