@@ -64,7 +64,7 @@ def apply_flow(handle, ff, shared=False):
         if leaf.table is not None:
             if leaf.table.shape[1] != 4:
                 raise LoweringError('leaf time tables have 4 columns')
-            arr[i].nt = leaf.table.shape[0]
+            arr[i].nt = getattr(leaf, 'nt', None) or leaf.table.shape[0]  # RadialGaussFFT: two stacked tables of nt rows
             arr[i].table_off = offset
             tables.append(leaf.table.reshape(-1))
             offset += leaf.table.size

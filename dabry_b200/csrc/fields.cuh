@@ -35,6 +35,12 @@ enum LeafKind : int32_t {
     LEAF_CHERTOVSKIH = 5,   //                                                :1089-1099
     LEAF_TRAP = 6,          // p[0]: rel_wid; table rows (ff_val, cx, cy, radius)   :1035-1086
     LEAF_RADIAL_GAUSS = 7,  // p: center(2), radius, sdev, v_max              :860-903
+    LEAF_TWO_SECTORS = 8,   // p: v_w1, v_w2, x_switch                        :565-598
+    LEAF_LINEAR_T = 9,      // table (3 rows): gradient_diff_time(4), gradient_init(4), origin(2) + value_origin(2)  :755-780
+    LEAF_RADIAL_GAUSS_T = 10,  // table: nt rows (cx, cy, radius, sdev) then nt rows (v_max, -, -, -)   :906-973
+    LEAF_BAND_GAUSS = 11,   // p: origin(2), unit vect(2), ampl, sdev; forward-difference Jacobian, dx 1e-6   :976-999
+    LEAF_BAND = 12,         // p: origin(2), unit vect(2), w_value(2), width; central differences, eps 1e-6   :1002-1032
+    LEAF_GYRE_MSEAS = 13,   // p: A, eps, T; central differences, eps 1e-6    :1102-1134
 };
 
 struct FieldLeaf {
@@ -70,6 +76,10 @@ struct Flow {  // w and J at one point
     double w0, w1, j00, j01, j10, j11;
 };
 
+struct D2v {
+    double x, y;
+};
+
 // ---------------------------------------------------------------------------------------------------------
 // FlowField._index (flowfield.py:152-175): lower frame and lerp coefficient of a time-tabulated parameter set
 DABRY_HD void time_index(const FieldLeaf& L, double t, int& i, double& alpha) {
@@ -94,10 +104,85 @@ DABRY_HD void time_index(const FieldLeaf& L, double t, int& i, double& alpha) {
     }
 }
 
+// Value of the leaves whose Jacobian the reference takes by finite differences (BandGaussFF, BandFF, GyreMSEASFF).
+// The differences amplify one ulp of the value 1e6 times, so products and sums are rounded one by one like numpy's.
+DABRY_HD_NOINLINE D2v fd_leaf_value(const FieldLeaf& L, double t, double x0, double x1) {
+    D2v o = {0., 0.};
+    if (L.kind == LEAF_BAND_GAUSS || L.kind == LEAF_BAND) {
+        const double d0 = sub_rn(x0, L.p[0]), d1 = sub_rn(x1, L.p[1]);
+        const double dist = fabs(sub_rn(mul_rn(L.p[2], d1), mul_rn(L.p[3], d0)));  // |cross(vect, x - origin)|
+        if (L.kind == LEAF_BAND_GAUSS) {
+            const double q = dist / L.p[5];
+            const double intensity = mul_rn(L.p[4], exp(mul_rn(-0.5, mul_rn(q, q))));
+            o.x = mul_rn(L.p[2], intensity);
+            o.y = mul_rn(L.p[3], intensity);
+        } else {
+            const double width = L.p[6], tw = width / 10;
+            const double outer = add_rn(width, tw / 2) / 2, inner = sub_rn(width, tw / 2) / 2;
+            if (dist >= outer) return o;
+            double f = 1.;
+            if (dist >= inner) f = sub_rn(1., sub_rn(dist, inner) / tw);
+            o.x = dist >= inner ? mul_rn(f, L.p[4]) : L.p[4];
+            o.y = dist >= inner ? mul_rn(f, L.p[5]) : L.p[5];
+        }
+    } else {  // LEAF_GYRE_MSEAS
+        const double A = L.p[0], eps = L.p[1], T = L.p[2];
+        const double a = mul_rn(eps, sin(mul_rn(mul_rn(2., M_PI), t) / T));
+        const double b = sub_rn(1., mul_rn(2., a));
+        const double f = add_rn(mul_rn(a, mul_rn(x0, x0)), mul_rn(b, x0));
+        const double dfdx = add_rn(mul_rn(mul_rn(2., a), x0), b);
+        const double pa = mul_rn(M_PI, A);
+        o.x = mul_rn(mul_rn(-pa, sin(mul_rn(M_PI, f))), cos(mul_rn(M_PI, x1)));
+        o.y = mul_rn(mul_rn(mul_rn(pa, cos(mul_rn(M_PI, f))), sin(mul_rn(M_PI, x1))), dfdx);
+    }
+    return o;
+}
+
 DABRY_HD void leaf_eval(const FieldLeaf& L, const double* __restrict__ tables, double t, double x0, double x1,
                         Flow& o) {
     o.w0 = o.w1 = o.j00 = o.j01 = o.j10 = o.j11 = 0.;
     switch (L.kind) {
+    case LEAF_TWO_SECTORS:  // np.heaviside(., 0.): 0 at the switch itself; the Jacobian is zero as written (:586-588)
+        o.w1 = L.p[0] * (L.p[2] - x0 > 0. ? 1. : 0.) + L.p[1] * (x0 - L.p[2] > 0. ? 1. : 0.);
+        break;
+    case LEAF_LINEAR_T: {
+        const double* q = tables + L.table_off;  // gradient_diff_time, gradient_init, origin, value_origin
+        const double m00 = q[0] * t + q[4], m01 = q[1] * t + q[5], m10 = q[2] * t + q[6], m11 = q[3] * t + q[7];
+        const double d0 = x0 - q[8], d1 = x1 - q[9];
+        o.w0 = (m00 * d0 + m01 * d1) + q[10];
+        o.w1 = (m10 * d0 + m11 * d1) + q[11];
+        o.j00 = m00;
+        o.j01 = m01;
+        o.j10 = m10;
+        o.j11 = m11;
+        break;
+    }
+    case LEAF_BAND_GAUSS: {  // forward differences, dx = 1e-6 (:995-999)
+        const double dx = 1e-6, k = 1 / dx;
+        const D2v v = fd_leaf_value(L, t, x0, x1);
+        const D2v vx = fd_leaf_value(L, t, add_rn(x0, dx), x1), vy = fd_leaf_value(L, t, x0, add_rn(x1, dx));
+        o.w0 = v.x;
+        o.w1 = v.y;
+        o.j00 = mul_rn(k, sub_rn(vx.x, v.x));
+        o.j10 = mul_rn(k, sub_rn(vx.y, v.y));
+        o.j01 = mul_rn(k, sub_rn(vy.x, v.x));
+        o.j11 = mul_rn(k, sub_rn(vy.y, v.y));
+        break;
+    }
+    case LEAF_BAND:
+    case LEAF_GYRE_MSEAS: {  // central differences, eps = 1e-6 (:1026-1032, :1128-1134)
+        const double eps = 1e-6, den = mul_rn(2., eps);
+        const D2v v = fd_leaf_value(L, t, x0, x1);
+        const D2v xp = fd_leaf_value(L, t, add_rn(x0, eps), x1), xm = fd_leaf_value(L, t, sub_rn(x0, eps), x1);
+        const D2v yp = fd_leaf_value(L, t, x0, add_rn(x1, eps)), ym = fd_leaf_value(L, t, x0, sub_rn(x1, eps));
+        o.w0 = v.x;
+        o.w1 = v.y;
+        o.j00 = sub_rn(xp.x, xm.x) / den;
+        o.j10 = sub_rn(xp.y, xm.y) / den;
+        o.j01 = sub_rn(yp.x, ym.x) / den;
+        o.j11 = sub_rn(yp.y, ym.y) / den;
+        break;
+    }
     case LEAF_UNIFORM:
         o.w0 = L.p[0];
         o.w1 = L.p[1];
@@ -224,9 +309,23 @@ DABRY_HD void leaf_eval(const FieldLeaf& L, const double* __restrict__ tables, d
         o.j11 = -ffv * (e1 * ds * e1 + q1 * s * q1);
         break;
     }
-    case LEAF_RADIAL_GAUSS: {
-        const double a = x0 - L.p[0], b = x1 - L.p[1];
-        const double radius = L.p[2], sdev = L.p[3], vmax = L.p[4];
+    case LEAF_RADIAL_GAUSS:
+    case LEAF_RADIAL_GAUSS_T: {
+        double cx = L.p[0], cy = L.p[1], radius = L.p[2], sdev = L.p[3], vmax = L.p[4];
+        if (L.kind == LEAF_RADIAL_GAUSS_T) {  // parameters lerped between the frames of FlowField._index (:937-950)
+            int i;
+            double al;
+            time_index(L, t, i, al);
+            const double* r0 = tables + L.table_off + 4 * i;
+            const double* r1 = r0 + 4;
+            const double* v0 = tables + L.table_off + 4 * (L.nt + i);
+            cx = (1 - al) * r0[0] + al * r1[0];
+            cy = (1 - al) * r0[1] + al * r1[1];
+            radius = (1 - al) * r0[2] + al * r1[2];
+            sdev = (1 - al) * r0[3] + al * r1[3];
+            vmax = (1 - al) * v0[0] + al * v0[4];
+        }
+        const double a = x0 - cx, b = x1 - cy;
         const double r = sqrt(a * a + b * b);
         if (r < 1e-3 * radius) break;
         const double e0 = a / r, e1 = b / r;

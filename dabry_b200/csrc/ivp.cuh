@@ -13,6 +13,12 @@ namespace dabry {
 
 #define DABRY_MAX_EVENTS (1 + DABRY_MAX_OBSTACLES)
 
+// DEFER builds (site.cuh DABRY_DEFER_RETRY): accepted steps a lane may run ahead of the slowest lane of its warp;
+// negative = unbounded
+#ifndef DABRY_DEFER_LEAD
+#define DABRY_DEFER_LEAD -1
+#endif
+
 enum IvpStatus : int32_t { IVP_FINISHED = 0, IVP_TERMINATED = 1, IVP_FAILED = -1, IVP_RUNNING = 2, IVP_DEFERRED = 3 };
 
 // Everything solve_ivp carries from one step to the next.  With a step budget the driver loop can be left after any
@@ -165,7 +171,38 @@ DABRY_HD void solve_ivp(const Rhs& rhs, Events& events, Sink& sink, double t0, d
     res.term_event = -1;
     res.t_term = 0.;
     bool finished = false;
-    while (!finished) {
+#if defined(__CUDA_ARCH__) && DABRY_DEFER_LEAD >= 0
+    // DEFER with a bounded lead: a lane may run at most DABRY_DEFER_LEAD accepted steps ahead of the slowest lane of its
+    // warp.  Lead 0 is scipy's inner retry loop as the lockstep warp executes it (everybody waits for every retry),
+    // an unbounded lead is plain DEFER (nobody waits, lanes drift apart by whole steps and the warp's gathers touch many
+    // cells); in between, the lanes whose attempt was accepted use the retry rounds of the others for their own next
+    // step.  The lanes that entered together vote at the top of every round; a lane that is done keeps voting until all are.
+    const unsigned members = DEFER ? __activemask() : 0u;
+    int steps_done = 0;
+#endif
+    for (;;) {
+#if defined(__CUDA_ARCH__) && DABRY_DEFER_LEAD >= 0
+        if (DEFER) {
+            if (!__ballot_sync(members, !finished)) break;
+#ifdef DABRY_DEFER_LEAD_T  // the lead measured in solver time (units of max_step) instead of accepted steps
+            // warp minimum of a double over an arbitrary member mask: order-preserving map to an unsigned 64-bit key,
+            // reduced in two 32-bit halves
+            unsigned long long key = (unsigned long long) __double_as_longlong(finished ? INFINITY : S.t);
+            key ^= (key >> 63) ? ~0ull : 0x8000000000000000ull;
+            const unsigned hi = (unsigned) (key >> 32), lo = (unsigned) key;
+            const unsigned hi_min = __reduce_min_sync(members, hi);
+            const unsigned lo_min = __reduce_min_sync(members, hi == hi_min ? lo : 0xffffffffu);
+            unsigned long long key_min = ((unsigned long long) hi_min << 32) | lo_min;
+            key_min ^= (key_min >> 63) ? 0x8000000000000000ull : ~0ull;
+            const double t_slowest = __longlong_as_double((long long) key_min);
+            if (finished || S.t > t_slowest + (DABRY_DEFER_LEAD_T) * max_step) continue;
+#else
+            const int slowest = __reduce_min_sync(members, finished ? 0x7fffffff : steps_done);
+            if (finished || steps_done > slowest + DABRY_DEFER_LEAD) continue;
+#endif
+        } else
+#endif
+        if (finished) break;
         // budget spent, or the time reached up to which the caller can serve the right-hand side: park between two steps
         if (carry && ((step_budget > 0 && steps_left-- == 0) || S.t >= t_park)) {
             carry->started = 1;
@@ -192,9 +229,18 @@ DABRY_HD void solve_ivp(const Rhs& rhs, Events& events, Sink& sink, double t0, d
             if (ok == 0) {
                 res.status = IVP_FAILED;
                 res.n_emitted = n_emitted;
+#if defined(__CUDA_ARCH__) && DABRY_DEFER_LEAD >= 0
+                if (DEFER) {  // keeps voting until the warp is done
+                    finished = true;
+                    continue;
+                }
+#endif
                 return;
             }
             if (DEFER && ok == 2) continue;  // rejected: the same step again in the next round, nothing else happened
+#if defined(__CUDA_ARCH__) && DABRY_DEFER_LEAD >= 0
+            ++steps_done;
+#endif
             if (S.t - tf >= 0.) finished = true;
         }
         const double t_old = S.t_old;

@@ -18,7 +18,8 @@ from dabry_b200.misc import Utils, Coords
 
 # leaf kinds of include/dabry_b200.h (enum dabry_leaf_kind)
 LEAF_UNIFORM, LEAF_STATE_LINEAR, LEAF_GYRE, LEAF_VORTEX, LEAF_RANKINE, LEAF_CHERTOVSKIH, LEAF_TRAP, \
-    LEAF_RADIAL_GAUSS = range(8)
+    LEAF_RADIAL_GAUSS, LEAF_TWO_SECTORS, LEAF_LINEAR_T, LEAF_RADIAL_GAUSS_T, LEAF_BAND_GAUSS, LEAF_BAND, \
+    LEAF_GYRE_MSEAS = range(14)
 
 
 class LoweringError(TypeError):
@@ -427,6 +428,9 @@ class TwoSectorsFF(FlowField):
     def d_value(self, t, x):
         return np.array([[0, 0], [0, 0]])
 
+    def _leaf(self):
+        return Leaf(LEAF_TWO_SECTORS, (self.v_w1, self.v_w2, self.x_switch))
+
 
 class TSEqualFF(TwoSectorsFF):
     def __init__(self, v_w1, v_w2, x_f):
@@ -583,6 +587,12 @@ class LinearFFT(FlowField):
     def d_value(self, t, x):
         return self.gradient_diff_time * t + self.gradient_init
 
+    def _leaf(self):
+        table = np.concatenate((np.asarray(self.gradient_diff_time, dtype=float).reshape(-1),
+                                np.asarray(self.gradient_init, dtype=float).reshape(-1),
+                                np.asarray(self.origin, dtype=float), np.asarray(self.value_origin, dtype=float)))
+        return Leaf(LEAF_LINEAR_T, table=table.reshape(3, 4))
+
 
 class PointSymFF(FlowField):
     """Point-symmetric linear field with divergence gamma and curl omega, Techy 2011 (flowfield.py:783-804)."""
@@ -718,6 +728,17 @@ class RadialGaussFFT(FlowField):
         center, radius, sdev, v_max = self._params(t)
         return _radial_gauss_jacobian(x, center, radius, sdev, v_max, self.zero_ceil)
 
+    def _leaf(self):
+        nt = self.radius.shape[0]
+        table = np.zeros((2 * nt, 4))
+        table[:nt, 0:2] = self.center
+        table[:nt, 2] = self.radius
+        table[:nt, 3] = self.sdev
+        table[nt:, 0] = self.v_max
+        leaf = Leaf(LEAF_RADIAL_GAUSS_T, table=table, t_start=self.t_start, t_end=self.t_end)
+        leaf.nt = nt
+        return leaf
+
 
 def _fd_jacobian_central(value, t, x, eps):
     ex, ey = eps * np.array((1, 0)), eps * np.array((0, 1))
@@ -745,6 +766,9 @@ class BandGaussFF(FlowField):
         return np.column_stack((1 / dx * (self.value(t, x + np.array((dx, 0.))) - self.value(t, x)),
                                 1 / dx * (self.value(t, x + np.array((0., dx))) - self.value(t, x))))
 
+    def _leaf(self):
+        return Leaf(LEAF_BAND_GAUSS, (self.origin[0], self.origin[1], self.vect[0], self.vect[1], self.ampl, self.sdev))
+
 
 class BandFF(FlowField):
     """Uniform jet of width `width` with linear edges; central-difference Jacobian, step 1e-6
@@ -771,6 +795,12 @@ class BandFF(FlowField):
 
     def d_value(self, t, x):
         return _fd_jacobian_central(self.value, t, x, 1e-6)
+
+    def _leaf(self):
+        w = np.asarray(self.w_value, dtype=float)
+        if w.shape != (2,):
+            raise LoweringError('BandFF on the device needs a 2-vector w_value')
+        return Leaf(LEAF_BAND, (self.origin[0], self.origin[1], self.vect[0], self.vect[1], w[0], w[1], self.width))
 
 
 class TrapFF(FlowField):
@@ -876,6 +906,9 @@ class GyreMSEASFF(FlowField):
 
     def d_value(self, t, x):
         return _fd_jacobian_central(self.value, t, x, 1e-6)
+
+    def _leaf(self):
+        return Leaf(LEAF_GYRE_MSEAS, (self.A, self.eps, self.T))
 
 
 def discretize_ff(ff: FlowField, nx=None, ny=None, nt=None, bl=None, tr=None):

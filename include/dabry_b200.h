@@ -91,7 +91,13 @@ enum dabry_leaf_kind {
     DABRY_LEAF_RANKINE = 4,      /* p: center(2), circulation, radius | table rows (cx, cy, gamma, radius)  :652-727 */
     DABRY_LEAF_CHERTOVSKIH = 5,  /*                                                  :1089-1099 */
     DABRY_LEAF_TRAP = 6,         /* p[0]: rel_wid; table rows (ff_val, cx, cy, radius)      :1035-1086 */
-    DABRY_LEAF_RADIAL_GAUSS = 7  /* p: center(2), radius, sdev, v_max                :860-903 */
+    DABRY_LEAF_RADIAL_GAUSS = 7, /* p: center(2), radius, sdev, v_max                :860-903 */
+    DABRY_LEAF_TWO_SECTORS = 8,  /* p: v_w1, v_w2, x_switch (TwoSectorsFF, TSEqualFF)  :565-598 */
+    DABRY_LEAF_LINEAR_T = 9,     /* table of 3 rows: gradient_diff_time(4), gradient_init(4), origin(2) value_origin(2)  :755-780 */
+    DABRY_LEAF_RADIAL_GAUSS_T = 10, /* table: nt rows (cx, cy, radius, sdev), then nt rows (v_max, 0, 0, 0)   :906-973 */
+    DABRY_LEAF_BAND_GAUSS = 11,  /* p: origin(2), unit vect(2), ampl, sdev; Jacobian by forward differences as written  :976-999 */
+    DABRY_LEAF_BAND = 12,        /* p: origin(2), unit vect(2), w_value(2), width; central differences as written  :1002-1032 */
+    DABRY_LEAF_GYRE_MSEAS = 13   /* p: A, eps, T; central differences as written     :1102-1134 */
 };
 
 typedef struct dabry_leaf {

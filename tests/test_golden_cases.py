@@ -19,7 +19,10 @@ from dump import solver_record
 # exactly srf.  Proven on the reference itself: oracle/tie_sensitivity.py moves the reference's right-hand side by
 # <= 1 ulp and lists the sites whose record changes (tests/golden/tie_sets.json).  These cases are compared site by
 # site on everything OUTSIDE that list (parity_util.compare_except_ties); all other cases are compared exactly.
-TIE_SENSITIVE = {'trap_R', 'chertovskih_T', 'gyre_T', 'gyre_rhoads2010_T', 'linear_T', 'moving_vortex_T',
+# `regional_discrete_penalty_R`: the reference differentiates the DiscretePenalty by central differences with
+# dx = 1e-8 (penalty.py:39-44), which amplifies one ulp of the interpolated value 5e7 times - 17 of its 150 sites move by
+# more than 1e-9 in the reference itself under the 1-ulp perturbation (24 of 24 seeded runs).
+TIE_SENSITIVE = {'regional_discrete_penalty_R', 'trap_R', 'chertovskih_T', 'gyre_T', 'gyre_rhoads2010_T', 'linear_T', 'moving_vortex_T',
                  'obstacle_T', 'point_symmetric_techy2011_T', 'spherical_geodesic_T', 'three_vortices_T', 'trap_T'}
 
 SITE_CASES = pu.golden_keys('R') + pu.golden_keys('T')

@@ -98,6 +98,53 @@ def analytic_rhs_parity():
         solver.close()
 
 
+def catalogue_fields_match_reference():
+    """The catalogue fields of flowfield.py:565-1134 (TwoSectors, TSEqual, LinearFFT, RadialGauss(T), BandGauss, Band,
+    GyreMSEAS, and a scaled sum of them) as device leaves against golden values of the UNMODIFIED reference's classes
+    (oracle/gen_field_golden.py -> tests/golden/analytic_fields.npz).  Tolerance: 1e-12 for the analytic Jacobians; the
+    finite-difference ones (dx = 1e-6 as written) amplify one ulp of exp / sin / cos 1e6 times -> 1e-8 absolute on
+    Jacobians of magnitude <= 25.  The host classes of this package must reproduce the reference bit for bit."""
+    import dabry_b200.flowfield as mine
+    from dabry_b200 import _lowering as low
+    from gen_field_golden import build, field_specs
+    g = np.load(os.path.join(pu.GOLDEN_DIR, 'analytic_fields.npz'))
+    specs = field_specs()
+    for name in specs:
+        if name.startswith('_'):
+            continue
+        ff = build(mine, name, specs)
+        t, x, w_ref, jac_ref = g[name + '_t'], g[name + '_x'], g[name + '_w'], g[name + '_jac']
+        w_host = np.array([np.asarray(ff.value(t[i], x[i]), dtype=float) for i in range(len(t))])
+        jac_host = np.array([np.asarray(ff.d_value(t[i], x[i]), dtype=float) for i in range(len(t))])
+        assert np.array_equal(w_host, w_ref) and np.array_equal(jac_host, jac_ref), ('host mirror', name)
+        handle = low.flow_evaluator(ff)
+        try:
+            w, jac = handle.eval_flow(t, x)
+        finally:
+            handle.close()
+        fd = name in ('band_gauss', 'band', 'gyre_mseas', 'sum_scaled')
+        assert np.max(np.abs(w - w_ref)) <= 1e-13 * max(1., np.abs(w_ref).max()), (name, np.max(np.abs(w - w_ref)))
+        tol = 1e-8 if fd else 1e-12
+        assert np.max(np.abs(jac - jac_ref)) <= tol * max(1., np.abs(jac_ref).max()), (name, np.max(np.abs(jac - jac_ref)))
+    with pytest.raises(mine.LoweringError):  # no Jacobian in the reference either (flowfield.py:836-857)
+        mine.DoubleGyreDampedFF(0.5, 0.5, 1., 1., 1., 0.5, 0.5, 0.3, 0.3).lower()
+    # and through a whole solve: a Gaussian jet across the route plus the unsteady double gyre, against the oracle
+    from dabry_b200.problem import NavigationProblem
+    from dabry_b200.solver_ef import SolverEFResampling
+    from solver_port import Port
+    ff = mine.BandGaussFF(np.array([0.5, 0.5]), np.array([0.2, 1.]), 0.6, 0.12) + 0.05 * mine.GyreMSEASFF()
+    pb = NavigationProblem(ff, np.array([0.1, 0.5]), np.array([0.9, 0.5]), 1., bl=np.array([0., 0.]),
+                           tr=np.array([1., 1.]), name='jet_and_gyre')
+    kw = dict(max_depth=2, n_costate_sectors=16, n_time=51)
+    port = Port(pb, 1.2, **kw).run_resampling()
+    solver = SolverEFResampling(pb, 1.2, **kw)
+    solver.solve()
+    rec, ref = solver_record(solver), pu.port_record(port)
+    pu.compare_sites_record(rec, ref, tol=1e-7)  # finite-difference Jacobians: 1 ulp of exp / sin -> 1e-10 per evaluation
+    assert solver.native_stats()['rk_steps'] == port.n_rk
+    solver.close()
+
+
 def rk4_fixed_matches_oracle():
     """Integrator RK4_FIXED == the oracle's scipy OdeSolver with the same stepper (events, obstacles, sphere)."""
     from dabry_b200.problem import NavigationProblem
@@ -213,6 +260,7 @@ def edge_cases():
 
 test_rhs_and_flow_parity_hostsim, test_rhs_and_flow_parity_gpu = _both(rhs_and_flow_parity)
 test_analytic_rhs_parity_hostsim, test_analytic_rhs_parity_gpu = _both(analytic_rhs_parity)
+test_catalogue_fields_hostsim, test_catalogue_fields_gpu = _both(catalogue_fields_match_reference)
 test_rk4_fixed_matches_oracle_hostsim, test_rk4_fixed_matches_oracle_gpu = _both(rk4_fixed_matches_oracle)
 test_f32_grid_within_tolerance_hostsim, test_f32_grid_within_tolerance_gpu = _both(f32_grid_within_tolerance)
 test_edge_cases_hostsim, test_edge_cases_gpu = _both(edge_cases)
