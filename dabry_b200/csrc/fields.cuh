@@ -21,6 +21,10 @@
 #define DABRY_COOP_FETCH 0
 #endif
 
+#ifndef DABRY_TRACE_CELL  // analysis hook of tests/hostsim (cell of every grid sample); nothing in the product
+#define DABRY_TRACE_CELL(frame, i0, j0)
+#endif
+
 namespace dabry {
 
 // FIELD_GRID_F32: the same pair records stored in fp32 (48 B per node, three 16-byte loads); arithmetic stays fp64
@@ -400,6 +404,7 @@ DABRY_HD void grid_eval(const GridDesc& G, double t, double x0, double x1, Flow&
     const int i0 = iclamp(ix, 0, G.nx - 1), i1 = iclamp(ix + 1, 0, G.nx - 1);
     const int j0 = iclamp(iy, 0, G.ny - 1), j1 = iclamp(iy + 1, 0, G.ny - 1);
     // record indices fit 32 bits (checked at upload); one 64-bit multiply per node for the byte offset
+    DABRY_TRACE_CELL(frame, i0, j0);
     const unsigned row0 = ((unsigned) frame * (unsigned) G.nx + (unsigned) i0) * (unsigned) G.ny;
     const unsigned row1 = ((unsigned) frame * (unsigned) G.nx + (unsigned) i1) * (unsigned) G.ny;
     // corner weights (w_t * w_x) * w_y in the reference; here the time factor is applied per node last

@@ -40,6 +40,30 @@ static FILE* hostsim_rk_trace_file() {
         if (FILE* tf_ = hostsim_rk_trace_file()) fprintf(tf_, "%d %.17g %.17g %.17g\n", (int) (n), (double) (t), (double) (h), (double) (error_norm)); \
     } while (0)
 
+// DABRY_HOSTSIM_TRACE_CELL=1: how often consecutive grid samples of the host thread fall into the same cell and frame
+// pair (what a per-thread cell cache would save); printed at exit
+struct HostsimCellStats {
+    long long samples = 0, same = 0, same_xy = 0;
+    int frame = -9, i0 = -9, j0 = -9;
+    bool on = getenv("DABRY_HOSTSIM_TRACE_CELL") != nullptr;
+    ~HostsimCellStats() {
+        if (on && samples) fprintf(stderr, "hostsim cells: %lld samples, same cell+frames as the previous sample %.4f, same cell %.4f\n",
+                                   samples, (double) same / samples, (double) same_xy / samples);
+    }
+};
+static HostsimCellStats g_cell_stats;
+#define DABRY_TRACE_CELL(f_, i_, j_)                                                                            \
+    do {                                                                                                        \
+        if (g_cell_stats.on) {                                                                                  \
+            ++g_cell_stats.samples;                                                                             \
+            if (g_cell_stats.i0 == (i_) && g_cell_stats.j0 == (j_)) {                                           \
+                ++g_cell_stats.same_xy;                                                                         \
+                if (g_cell_stats.frame == (f_)) ++g_cell_stats.same;                                            \
+            }                                                                                                   \
+            g_cell_stats.frame = (f_); g_cell_stats.i0 = (i_); g_cell_stats.j0 = (j_);                          \
+        }                                                                                                       \
+    } while (0)
+
 #include "../../dabry_b200/csrc/engine.cuh"
 
 namespace dabry {
