@@ -34,7 +34,7 @@ def apply_flow(handle, ff, shared=False):
         # host-supplied Jacobian samples (DiscreteFF.from_ff) are uploaded; the default central differences
         # (flowfield.py:474-504) are recomputed on the device instead of being shipped
         grad = None
-        if inner.grad_values is not None and not inner.grad_is_device_default():
+        if inner.has_host_jacobian():
             grad = nat.f64(inner.grad_values)
         b = np.asarray(inner.bounds, dtype=float)
         lo = nat.f64(np.concatenate(((0.,), b[:, 0])) if not unsteady else b[:, 0])

@@ -186,8 +186,10 @@ class DiscreteFF(FlowField):
         self._grad_is_default = False
         self._grad_fingerprint = None
         self.grad_values = grad_values
-        if not force_no_diff and self.grad_values is None:
-            self.compute_derivatives()
+        # The reference differentiates the samples in its constructor (flowfield.py:209-210).  Here the device does that
+        # at upload (PackGridPhase), so the host copy of the default Jacobian - 2 x the size of `values` - is only
+        # computed when somebody reads `grad_values` on the host (d_value, save, the oracle): same values, on demand.
+        self._grad_lazy = not force_no_diff and grad_values is None
         if values.ndim == 3:
             self.value = self._value_steady
             self.d_value = self._d_value_steady
@@ -199,6 +201,9 @@ class DiscreteFF(FlowField):
 
     @property
     def grad_values(self):
+        if self._grad_values is None and getattr(self, '_grad_lazy', False):
+            self._grad_lazy = False
+            self.compute_derivatives()
         return self._grad_values
 
     @grad_values.setter
@@ -208,6 +213,8 @@ class DiscreteFF(FlowField):
         self._grad_values = value
         self._grad_is_default = False
         self._grad_fingerprint = None
+        if value is not None:
+            self._grad_lazy = False
 
     @staticmethod
     def _fingerprint(a):
@@ -217,8 +224,13 @@ class DiscreteFF(FlowField):
     def grad_is_device_default(self):
         """True when `grad_values` is still exactly what `compute_derivatives` produced (same array, not edited in
         place as far as a strided fingerprint of 4 096 entries can tell): the device then differentiates by itself."""
-        return bool(self._grad_is_default and self._grad_values is not None
-                    and self._grad_fingerprint == self._fingerprint(self._grad_values))
+        if self._grad_values is None:
+            return bool(getattr(self, '_grad_lazy', False))  # never materialised on the host: the device's own
+        return bool(self._grad_is_default and self._grad_fingerprint == self._fingerprint(self._grad_values))
+
+    def has_host_jacobian(self):
+        """True when a caller-supplied (or edited) Jacobian must be uploaded; does not trigger the lazy default."""
+        return self._grad_values is not None and not self.grad_is_device_default()
 
     @property
     def times(self):
@@ -237,17 +249,22 @@ class DiscreteFF(FlowField):
         if not self.values.flags['WRITEABLE']:
             self.values = self.values.copy()
         pins = [nat.PinnedArray(self.values)]
-        if self.grad_values is not None and not self.grad_is_device_default():
-            self.grad_values = np.array(self.grad_values, dtype=np.float64, order='C', copy=None)
-            pins.append(nat.PinnedArray(self.grad_values))
+        if self.has_host_jacobian():
+            self.grad_values = np.array(self._grad_values, dtype=np.float64, order='C', copy=None)
+            pins.append(nat.PinnedArray(self._grad_values))
         self._pins = pins
         return self
 
     @classmethod
-    def from_npz(cls, filepath):
-        """Flow file of docs/flow_format.md: arrays `values`, `bounds`, `coords` (flowfield.py:222-225)."""
+    def from_npz(cls, filepath, pin=False):
+        """Flow file of docs/flow_format.md: arrays `values`, `bounds`, `coords` (flowfield.py:222-225).
+        pin=True (no reference counterpart): the samples are read straight into a contiguous float64 array that is
+        page-locked in place, i.e. ready for the streamed upload of `dabry_set_flow_grid`; the Jacobian is left to the
+        device and only materialised on the host if `grad_values` is read."""
         with np.load(filepath) as data:
-            return cls(data['values'], data['bounds'], Coords.from_string(data['coords']))
+            values = np.ascontiguousarray(data['values'], dtype=np.float64)
+            ff = cls(values, data['bounds'], Coords.from_string(data['coords']))
+        return ff.pin_memory() if pin else ff
 
     @classmethod
     def from_h5(cls, filepath, **kwargs):

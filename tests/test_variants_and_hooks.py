@@ -674,6 +674,42 @@ def exporters_against_oracle():
 test_exporters_against_oracle_hostsim, test_exporters_against_oracle_gpu = _both(exporters_against_oracle)
 
 
+def test_lazy_host_jacobian_and_npz_ingest(hostsim, tmp_path):
+    """DiscreteFF: the default Jacobian (flowfield.py:474-504) is computed on the host only when read - same values as
+    the reference's eager constructor -, a solve never materialises it (the device differentiates at upload), a
+    caller-supplied Jacobian is uploaded; `from_npz` round trip of docs/flow_format.md."""
+    from dabry_b200 import synthetic
+    from dabry_b200.flowfield import DiscreteFF, save_ff
+    from dabry_b200.misc import Coords
+    from dabry_b200.problem import NavigationProblem
+    from dabry_b200.solver_ef import SolverEFResampling
+    sc = synthetic.planar_waves(5, 24, 20)
+    ff = DiscreteFF(sc.values, sc.bounds, Coords.CARTESIAN)
+    assert ff._grad_values is None and ff.grad_is_device_default() and not ff.has_host_jacobian()
+    eager = DiscreteFF(sc.values, sc.bounds, Coords.CARTESIAN, force_no_diff=True)
+    eager.compute_derivatives()
+    pb = NavigationProblem(ff, sc.x_init, sc.x_target, sc.srf, bl=sc.bl, tr=sc.tr, name='lazy').rescale()
+    solver = SolverEFResampling(pb, sc.total_duration, n_costate_sectors=12, max_depth=1)
+    solver.solve()
+    cost = solver.solution_cost
+    solver.close()
+    assert ff._grad_values is None, 'the solve materialised the host Jacobian'
+    assert np.array_equal(ff.grad_values, eager.grad_values) and ff.grad_is_device_default()
+    # the same field with the Jacobian handed over by the caller: uploaded, same result
+    custom = DiscreteFF(sc.values, sc.bounds, Coords.CARTESIAN, grad_values=eager.grad_values.copy())
+    assert custom.has_host_jacobian()
+    pb2 = NavigationProblem(custom, sc.x_init, sc.x_target, sc.srf, bl=sc.bl, tr=sc.tr, name='custom').rescale()
+    solver = SolverEFResampling(pb2, sc.total_duration, n_costate_sectors=12, max_depth=1)
+    solver.solve()
+    assert solver.solution_cost == cost
+    solver.close()
+    path = str(tmp_path / 'ff.npz')
+    save_ff(ff, path)
+    back = DiscreteFF.from_npz(path)
+    assert np.array_equal(back.values, ff.values) and np.array_equal(back.bounds, ff.bounds) and back.coords == ff.coords
+    assert back._grad_values is None and back.values.flags['C_CONTIGUOUS'] and back.values.dtype == np.float64
+
+
 def test_root_fan_matches_numpy_and_shards():
     """The threaded, cached root fan equals the reference's expression 1000 (cos, sin)(linspace) bit for bit
     (solver_ef.py:465-467), and a block-cyclic shard is the matching subset of the ring."""
