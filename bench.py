@@ -695,7 +695,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         kind = 'reference' if reference_installed() else 'port'
         cores = cpu_cores()
-        per_core = (args.cpu_sample_roots // cores) if args.cpu_sample_roots else (16 if kind == 'reference' else 48)
+        per_core = (args.cpu_sample_roots // cores) if args.cpu_sample_roots else (64 if kind == 'reference' else 160)  # ~10 s of CPU work
         pool = CpuPool(args.workload, args.small, cores, kind)
         try:
             rate, steps, busy, per = pool.run(w.n_roots, per_core * cores)

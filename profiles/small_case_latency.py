@@ -1,5 +1,5 @@
 """Time-to-solution of the reference's own small cases (30 roots, default depth) on the GPU: these are latency-bound
-(every launch has a few hundred threads).  Run on a GPU box:  python profiles/small_case_latency.py"""
+(every launch has a few hundred threads).  Run on a GPU box:  python profiles/small_case_latency.py [case ...]"""
 import os
 import sys
 import time
@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dabry_b200.problem import NavigationProblem  # noqa: E402
 from dabry_b200.solver_ef import SolverEFResampling, SolverEFTrimming  # noqa: E402
 
-for name in ('movor', 'three_vortices', 'gyre', 'obstacle'):
+for name in (sys.argv[1:] or ('movor', 'three_vortices', 'gyre', 'obstacle')):
     for cls in (SolverEFResampling, SolverEFTrimming):
         pb = NavigationProblem.from_name(name).rescale()
         best = None
