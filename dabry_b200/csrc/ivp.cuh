@@ -225,7 +225,9 @@ DABRY_HD void solve_ivp(const Rhs& rhs, Events& events, Sink& sink, double t0, d
             finished = true;
         } else {
             const int ok = METHOD == METHOD_RK4 ? (int) rk4_step<N>(S, rhs, tf, max_step, n_attempts)
-                                                : rk_step<N, DEFER>(S, rhs, tf, max_step, rtol, atol, n_attempts);
+                           : (DABRY_ROLLED_STAGES && N == 4 && !DEFER)
+                               ? rk_step_rolled<N>(S, rhs, tf, max_step, rtol, atol, n_attempts)
+                               : rk_step<N, DEFER>(S, rhs, tf, max_step, rtol, atol, n_attempts);
             if (ok == 0) {
                 res.status = IVP_FAILED;
                 res.n_emitted = n_emitted;

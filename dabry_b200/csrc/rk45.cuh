@@ -237,6 +237,105 @@ DABRY_HD int rk_step(RkState<N, KS>& S, const Rhs& rhs, double t_bound, double m
     return 1;
 }
 
+// ---- rolled variant of the step (experiment, DABRY_ROLLED_STAGES) ---------------------------------------
+// The six stage evaluations as ONE loop body: the right-hand side appears once in the step (it can then be inlined
+// without multiplying the code by six), the tableau row is read from constant memory by stage index, and the stage
+// values are addressed by stage index - i.e. they live in local or shared memory (KS) instead of registers.  Row 6 of
+// the table is b (FSAL: y_new is the sixth combination, f(t + h, y_new) the seventh stage).  Same sums in the same
+// order as rk_step; zero coefficients are kept in the sums, as numpy's dot keeps them.
+#ifndef DABRY_ROLLED_STAGES
+#define DABRY_ROLLED_STAGES 0
+#endif
+struct DormandPrinceRows {
+    double a[6][6];  // row s - 1: coefficients of K[0..s-1] for stage s = 1..5, row 5: b
+    double c[6];
+};
+#define DABRY_DP_ROWS_INIT {{{1. / 5., 0., 0., 0., 0., 0.}, {3. / 40., 9. / 40., 0., 0., 0., 0.}, {44. / 45., -56. / 15., 32. / 9., 0., 0., 0.}, {19372. / 6561., -25360. / 2187., 64448. / 6561., -212. / 729., 0., 0.}, {9017. / 3168., -355. / 33., 46732. / 5247., 49. / 176., -5103. / 18656., 0.}, {35. / 384., 0., 500. / 1113., 125. / 192., -2187. / 6784., 11. / 84.}}, {1. / 5., 3. / 10., 4. / 5., 8. / 9., 1., 1.}}
+#if defined(__CUDACC__)
+__constant__ DormandPrinceRows c_dp_rows = DABRY_DP_ROWS_INIT;
+#endif
+static const DormandPrinceRows h_dp_rows = DABRY_DP_ROWS_INIT;
+#if defined(__CUDA_ARCH__)
+#define DPR (c_dp_rows)
+#else
+#define DPR (h_dp_rows)
+#endif
+
+template <int N, class KS, class Rhs>
+DABRY_HD int rk_step_rolled(RkState<N, KS>& S, const Rhs& rhs, double t_bound, double max_step, double rtol, double atol,
+                            unsigned& n_attempts) {
+    const double t = S.t;
+    double h_abs = S.h_abs;
+    const double safe = 1e-12 * (fabs(t) + 1.);
+    bool rejected = false;
+    if (h_abs > max_step) h_abs = max_step;
+    else if (!(h_abs > safe) && h_abs < 10. * ulp_above(t)) h_abs = 10. * ulp_above(t);
+#pragma unroll
+    for (int i = 0; i < N; ++i) S.K[0][i] = S.K[6][i];  // FSAL
+    double y_new[N];
+    for (;;) {
+        if (!(h_abs > safe) && h_abs < 10. * ulp_above(t)) return 0;
+        double t_new = t + h_abs;
+        if (t_new - t_bound > 0.) t_new = t_bound;
+        const double h = t_new - t;
+        h_abs = fabs(h);
+        ++n_attempts;
+#pragma unroll 1
+        for (int s = 1; s <= 6; ++s) {
+            double acc[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) acc[i] = DPR.a[s - 1][0] * S.K[0][i];
+#pragma unroll 1
+            for (int j = 1; j < s; ++j) {
+                const double a = DPR.a[s - 1][j];
+#pragma unroll
+                for (int i = 0; i < N; ++i) acc[i] = acc[i] + a * S.K[j][i];
+            }
+            double ks[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) y_new[i] = S.y[i] + acc[i] * h;
+            rhs(s < 5 ? t + DPR.c[s - 1] * h : t + h, y_new, ks);
+#pragma unroll
+            for (int i = 0; i < N; ++i) S.K[s][i] = ks[i];
+        }
+        double err[N], scale[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            err[i] = (DP(e1) * S.K[0][i] + DP(e3) * S.K[2][i] + DP(e4) * S.K[3][i]
+                      + DP(e5) * S.K[4][i] + DP(e6) * S.K[5][i] + DP(e7) * S.K[6][i]) * h;
+            scale[i] = atol + dmax(fabs(S.y[i]), fabs(y_new[i])) * rtol;
+        }
+        const double error_norm = rms_norm_scaled<N>(err, scale);
+        DABRY_TRACE_RK_ATTEMPT(N, t, h, error_norm);
+        if (error_norm < 1.) {
+            const double r = max_step / h_abs;
+            const double q = DABRY_RK_SAFETY / r;
+            const double q2 = q * q;
+            if (!rejected && r <= DABRY_RK_MAX_FACTOR && error_norm < 0.99 * (q2 * q2 * q)) {
+                h_abs = max_step;
+            } else {
+                double factor;
+                if (error_norm == 0.) factor = DABRY_RK_MAX_FACTOR;
+                else factor = dmin(DABRY_RK_MAX_FACTOR, DABRY_RK_SAFETY * pow(error_norm, -0.2));
+                if (rejected) factor = dmin(1., factor);
+                h_abs *= factor;
+            }
+            S.t_old = t;
+            S.t = t_new;
+            break;
+        }
+        h_abs *= dmax(DABRY_RK_MIN_FACTOR, DABRY_RK_SAFETY * pow(error_norm, -0.2));
+        rejected = true;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        S.K[7][i] = S.y[i];
+        S.y[i] = y_new[i];
+    }
+    S.h_abs = h_abs;
+    return 1;
+}
+
 // Quartic dense output of the last accepted step (rk.py:178-180, 715-737): Q = K^T P, P from rk.py:553-565.
 template <int N>
 struct Dense {
