@@ -167,7 +167,10 @@ struct FreeArcPhase {  // the hot kernel: one thread per extremal, free arc with
     DABRY_HD void operator()(int64_t i) const {
         const int s = list ? list[i] : base + (int) i;
         unsigned attempts = 0, calls = 0;
-        site_free_arc<FK, METHOD, CHUNKED>(problem(), S, s, index_t, attempts, calls, budget, t_park, resume_only != 0);
+        // the throughput build of a gridded field runs the rolled step (site.cuh DABRY_FAST_STEP)
+        constexpr bool kFast = LEAN && DABRY_FAST_STEP != 0 && FK != FIELD_PROGRAM;
+        site_free_arc<FK, METHOD, CHUNKED, kFast>(problem(), S, s, index_t, attempts, calls, budget, t_park,
+                                                  resume_only != 0);
         DABRY_TRACE_FREE_ARC(s, attempts);
         counter_add(&counters->rk_steps, attempts);
         counter_add(&counters->rk_steps_free, attempts);

@@ -133,7 +133,8 @@ DABRY_HD_NOINLINE EventStep<N> event_step(const Dense<N> D, Events& events, Sink
 // Events concept:  int count() const;  bool terminal(int e) const;  double value(int e, double t, const double* y) const;
 //                  void record(int e, double t_root);
 // Sink concept:    void emit(int j, double t, const double* y);     j indexes the un-sliced linspace
-template <int N, int METHOD, class KS = KRegisters<N>, bool DEFER = false, class Rhs, class Events, class Sink>
+template <int N, int METHOD, class KS = KRegisters<N>, bool DEFER = false, bool ROLLED = false, class Rhs, class Events,
+          class Sink>
 DABRY_HD void solve_ivp(const Rhs& rhs, Events& events, Sink& sink, double t0, double tf, const double* y0,
                         const EvalGrid& grid, double max_step, double rtol, double atol, IvpResult<N>& res,
                         unsigned& n_attempts, IvpCarry<N>* carry = nullptr, int step_budget = 0, KS kstore = KS(),
@@ -219,15 +220,19 @@ DABRY_HD void solve_ivp(const Rhs& rhs, Events& events, Sink& sink, double t0, d
             res.n_emitted = n_emitted;
             return;
         }
+        Dense<N> D;  // the rolled step builds the interpolant of the step it accepts itself
+        bool have_dense = false;
         // OdeSolver.step (base.py): a solver already at t_bound finishes without stepping
         if (S.t == tf) {
             S.t_old = S.t;
             finished = true;
         } else {
             const int ok = METHOD == METHOD_RK4 ? (int) rk4_step<N>(S, rhs, tf, max_step, n_attempts)
-                           : (DABRY_ROLLED_STAGES && N == 4 && !DEFER)
-                               ? rk_step_rolled<N>(S, rhs, tf, max_step, rtol, atol, n_attempts)
+                           : (ROLLED && !DEFER)
+                               ? rk_step_rolled<N>(S, rhs, tf, max_step, rtol, atol, n_attempts,
+                                                   (DABRY_FAST_KEEP & 4) ? &D : nullptr)
                                : rk_step<N, DEFER>(S, rhs, tf, max_step, rtol, atol, n_attempts);
+            have_dense = (DABRY_FAST_KEEP & 4) && ROLLED && !DEFER && METHOD != METHOD_RK4 && ok == 1;
             if (ok == 0) {
                 res.status = IVP_FAILED;
                 res.n_emitted = n_emitted;
@@ -258,9 +263,10 @@ DABRY_HD void solve_ivp(const Rhs& rhs, Events& events, Sink& sink, double t0, d
         // the local interpolant is needed for event roots and for the t_eval samples inside this step
         const bool sample_due = eval_i < grid.n && grid.at(eval_i) <= t;
         if (na == 0 && !sample_due) continue;
-        Dense<N> D;
-        if (METHOD == METHOD_RK4) rk4_dense<N>(S, D);
-        else rk_dense<N>(S, D);
+        if (!have_dense) {
+            if (METHOD == METHOD_RK4) rk4_dense<N>(S, D);
+            else rk_dense<N>(S, D);
+        }
         if (na == 0) {
             // common path, no call in it: the interpolant stays in registers (with the root finder in the same scope it
             // was written to local memory and read back on every step: 34 LDL/STL per accepted step)

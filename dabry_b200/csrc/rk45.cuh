@@ -44,17 +44,41 @@ struct KRegisters {
     double v[8][N];
     DABRY_HD double* operator[](int a) { return v[a]; }
     DABRY_HD const double* operator[](int a) const { return v[a]; }
+    DABRY_HD void load_row(int a, double* out) const {
+#pragma unroll
+        for (int i = 0; i < N; ++i) out[i] = v[a][i];
+    }
+    DABRY_HD void store_row(int a, const double* in) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[a][i] = in[i];
+    }
 };
 
 #if defined(__CUDACC__)
+// Layout: tile[row][pair][thread] of 16-byte pairs (components 2 * pair, 2 * pair + 1), so that a row of a thread is
+// N / 2 conflict-free 128-bit accesses (a quarter-warp covers 128 contiguous bytes).
 template <int N, int THREADS>
 struct KShared {
-    double* base;  // &tile[threadIdx.x], tile = double[8 * N * THREADS] in shared memory
+    double* base;  // (double*) &tile2[threadIdx.x], tile2 = double2[8 * (N / 2) * THREADS] in shared memory
     struct Row {
         double* p;
-        __device__ double& operator[](int i) const { return p[i * THREADS]; }
+        __device__ double& operator[](int i) const { return p[(i >> 1) * (2 * THREADS) + (i & 1)]; }
     };
     __device__ Row operator[](int a) const { return Row{base + a * (N * THREADS)}; }
+    __device__ void load_row(int a, double* out) const {
+        const double2* q = reinterpret_cast<const double2*>(base + a * (N * THREADS));
+#pragma unroll
+        for (int k = 0; k < N / 2; ++k) {
+            const double2 v = q[k * THREADS];
+            out[2 * k] = v.x;
+            out[2 * k + 1] = v.y;
+        }
+    }
+    __device__ void store_row(int a, const double* in) const {
+        double2* q = reinterpret_cast<double2*>(base + a * (N * THREADS));
+#pragma unroll
+        for (int k = 0; k < N / 2; ++k) q[k * THREADS] = make_double2(in[2 * k], in[2 * k + 1]);
+    }
 };
 #endif
 
@@ -237,15 +261,24 @@ DABRY_HD int rk_step(RkState<N, KS>& S, const Rhs& rhs, double t_bound, double m
     return 1;
 }
 
-// ---- rolled variant of the step (experiment, DABRY_ROLLED_STAGES) ---------------------------------------
-// The six stage evaluations as ONE loop body: the right-hand side appears once in the step (it can then be inlined
-// without multiplying the code by six), the tableau row is read from constant memory by stage index, and the stage
-// values are addressed by stage index - i.e. they live in local or shared memory (KS) instead of registers.  Row 6 of
-// the table is b (FSAL: y_new is the sixth combination, f(t + h, y_new) the seventh stage).  Same sums in the same
-// order as rk_step; zero coefficients are kept in the sums, as numpy's dot keeps them.
-#ifndef DABRY_ROLLED_STAGES
-#define DABRY_ROLLED_STAGES 0
-#endif
+// Coefficients of the local interpolant of a step (filled by rk_dense / rk4_dense / rk_step_rolled).
+template <int N>
+struct Dense {
+    double t_old, h;
+    double y_old[N];
+    double Q[N][4];
+};
+
+// ---- rolled variant of the step (the throughput kernel of gridded fields, site.cuh DABRY_FAST_STEP) -------------------
+// The six stage evaluations as ONE loop body: the right-hand side appears once in the step, so it can be inlined without
+// multiplying the code by six (no call, no argument marshalling, its loads scheduled with the stage sums); the tableau
+// row is read from constant memory by stage index, and the stage values are addressed by stage index - they live in
+// shared memory (KShared: two 128-bit accesses per row) instead of registers, which the right-hand side then has to
+// itself.  Row 6 of the table is b (FSAL: y_new is the sixth combination, f(t + h, y_new) the seventh stage).  Same sums
+// in the same order as rk_step; zero coefficients stay in the sums, as numpy's dot keeps them.  Measured (B200, config 4):
+// 24.7 vs 25.5 ms for the unrolled step with a non-inlined right-hand side, config 3 14.1 vs 16.2 ms
+// (profiles/r02_ab_rolled.txt); the same loop with the stage values in registers behind a switch, or in local memory, or
+// with a called right-hand side is slower than the unrolled step (32.2 / 27.9 / 27.1 ms).
 struct DormandPrinceRows {
     double a[6][6];  // row s - 1: coefficients of K[0..s-1] for stage s = 1..5, row 5: b
     double c[6];
@@ -261,18 +294,28 @@ static const DormandPrinceRows h_dp_rows = DABRY_DP_ROWS_INIT;
 #define DPR (h_dp_rows)
 #endif
 
+// DABRY_FAST_KEEP: what the rolled step keeps in registers besides shared memory - 1: K[0] (read by every stage),
+// 2: the row the last right-hand side produced (the last term of the next stage's sum), 4: the rows of the error estimate
+// for the interpolant of the accepted step (built inside the step instead of by rk_dense).
+#ifndef DABRY_FAST_KEEP
+#define DABRY_FAST_KEEP 3
+#endif
+// dense: when not null, the interpolant of the accepted step is built here, from the rows the error estimate has just
+// read (rk_dense would read the same six rows from shared memory again).
 template <int N, class KS, class Rhs>
 DABRY_HD int rk_step_rolled(RkState<N, KS>& S, const Rhs& rhs, double t_bound, double max_step, double rtol, double atol,
-                            unsigned& n_attempts) {
+                            unsigned& n_attempts, Dense<N>* dense = nullptr) {
     const double t = S.t;
     double h_abs = S.h_abs;
     const double safe = 1e-12 * (fabs(t) + 1.);
     bool rejected = false;
     if (h_abs > max_step) h_abs = max_step;
     else if (!(h_abs > safe) && h_abs < 10. * ulp_above(t)) h_abs = 10. * ulp_above(t);
-#pragma unroll
-    for (int i = 0; i < N; ++i) S.K[0][i] = S.K[6][i];  // FSAL
+    double k0[N];  // FSAL: f(t, y) of the last accepted step
+    S.K.load_row(6, k0);
+    S.K.store_row(0, k0);
     double y_new[N];
+    double q6[N], q2[N], q3[N], q4[N], q5[N];  // rows of the accepted attempt, for the interpolant
     for (;;) {
         if (!(h_abs > safe) && h_abs < 10. * ulp_above(t)) return 0;
         double t_new = t + h_abs;
@@ -281,29 +324,65 @@ DABRY_HD int rk_step_rolled(RkState<N, KS>& S, const Rhs& rhs, double t_bound, d
         h_abs = fabs(h);
         ++n_attempts;
 #pragma unroll 1
+        double ks[N];  // the row the last right-hand side produced
+#pragma unroll 1
         for (int s = 1; s <= 6; ++s) {
             double acc[N];
+            {
+                double r0[N];
+                if (DABRY_FAST_KEEP & 1) {
 #pragma unroll
-            for (int i = 0; i < N; ++i) acc[i] = DPR.a[s - 1][0] * S.K[0][i];
-#pragma unroll 1
-            for (int j = 1; j < s; ++j) {
-                const double a = DPR.a[s - 1][j];
+                    for (int i = 0; i < N; ++i) r0[i] = k0[i];
+                } else {
+                    S.K.load_row(0, r0);
+                }
 #pragma unroll
-                for (int i = 0; i < N; ++i) acc[i] = acc[i] + a * S.K[j][i];
+                for (int i = 0; i < N; ++i) acc[i] = DPR.a[s - 1][0] * r0[i];
             }
-            double ks[N];
+            const int j_end = (DABRY_FAST_KEEP & 2) ? s - 1 : s;  // the last term comes from registers
+#pragma unroll 1
+            for (int j = 1; j < j_end; ++j) {
+                const double a = DPR.a[s - 1][j];
+                double kj[N];
+                S.K.load_row(j, kj);
+#pragma unroll
+                for (int i = 0; i < N; ++i) acc[i] = acc[i] + a * kj[i];
+            }
+            if ((DABRY_FAST_KEEP & 2) && s >= 2) {
+                const double a = DPR.a[s - 1][s - 1];
+#pragma unroll
+                for (int i = 0; i < N; ++i) acc[i] = acc[i] + a * ks[i];
+            }
 #pragma unroll
             for (int i = 0; i < N; ++i) y_new[i] = S.y[i] + acc[i] * h;
             rhs(s < 5 ? t + DPR.c[s - 1] * h : t + h, y_new, ks);
-#pragma unroll
-            for (int i = 0; i < N; ++i) S.K[s][i] = ks[i];
+            S.K.store_row(s, ks);
         }
         double err[N], scale[N];
+        {
+            double r0[N];
+            if (DABRY_FAST_KEEP & 1) {
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-            err[i] = (DP(e1) * S.K[0][i] + DP(e3) * S.K[2][i] + DP(e4) * S.K[3][i]
-                      + DP(e5) * S.K[4][i] + DP(e6) * S.K[5][i] + DP(e7) * S.K[6][i]) * h;
-            scale[i] = atol + dmax(fabs(S.y[i]), fabs(y_new[i])) * rtol;
+                for (int i = 0; i < N; ++i) r0[i] = k0[i];
+            } else {
+                S.K.load_row(0, r0);
+            }
+            S.K.load_row(2, q2);
+            S.K.load_row(3, q3);
+            S.K.load_row(4, q4);
+            S.K.load_row(5, q5);
+            if (DABRY_FAST_KEEP & 2) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) q6[i] = ks[i];
+            } else {
+                S.K.load_row(6, q6);
+            }
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                err[i] = (DP(e1) * r0[i] + DP(e3) * q2[i] + DP(e4) * q3[i] + DP(e5) * q4[i] + DP(e6) * q5[i]
+                          + DP(e7) * q6[i]) * h;
+                scale[i] = atol + dmax(fabs(S.y[i]), fabs(y_new[i])) * rtol;
+            }
         }
         const double error_norm = rms_norm_scaled<N>(err, scale);
         DABRY_TRACE_RK_ATTEMPT(N, t, h, error_norm);
@@ -327,31 +406,56 @@ DABRY_HD int rk_step_rolled(RkState<N, KS>& S, const Rhs& rhs, double t_bound, d
         h_abs *= dmax(DABRY_RK_MIN_FACTOR, DABRY_RK_SAFETY * pow(error_norm, -0.2));
         rejected = true;
     }
+    if (dense) {  // rk_dense on the rows still in registers; y_old is the state the step started from
+        dense->t_old = S.t_old;
+        dense->h = S.t - S.t_old;
+        double r0[N];
+        if (DABRY_FAST_KEEP & 1) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-        S.K[7][i] = S.y[i];
-        S.y[i] = y_new[i];
+            for (int i = 0; i < N; ++i) r0[i] = k0[i];
+        } else {
+            S.K.load_row(0, r0);
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            dense->y_old[i] = S.y[i];
+            const double c0 = r0[i], c2 = q2[i], c3 = q3[i], c4 = q4[i], c5 = q5[i], c6 = q6[i];
+            dense->Q[i][0] = c0;
+            dense->Q[i][1] = DP(p11) * c0 + DP(p13) * c2 + DP(p14) * c3 + DP(p15) * c4 + DP(p16) * c5 + DP(p17) * c6;
+            dense->Q[i][2] = DP(p21) * c0 + DP(p23) * c2 + DP(p24) * c3 + DP(p25) * c4 + DP(p26) * c5 + DP(p27) * c6;
+            dense->Q[i][3] = DP(p31) * c0 + DP(p33) * c2 + DP(p34) * c3 + DP(p35) * c4 + DP(p36) * c5 + DP(p37) * c6;
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) S.y[i] = y_new[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            S.K[7][i] = S.y[i];
+            S.y[i] = y_new[i];
+        }
     }
     S.h_abs = h_abs;
     return 1;
 }
 
 // Quartic dense output of the last accepted step (rk.py:178-180, 715-737): Q = K^T P, P from rk.py:553-565.
-template <int N>
-struct Dense {
-    double t_old, h;
-    double y_old[N];
-    double Q[N][4];
-};
 
 template <int N, class KS>
 DABRY_HD void rk_dense(const RkState<N, KS>& S, Dense<N>& D) {
     D.t_old = S.t_old;
     D.h = S.t - S.t_old;
+    double r0[N], r2[N], r3[N], r4[N], r5[N], r6[N], r7[N];
+    S.K.load_row(0, r0);
+    S.K.load_row(2, r2);
+    S.K.load_row(3, r3);
+    S.K.load_row(4, r4);
+    S.K.load_row(5, r5);
+    S.K.load_row(6, r6);
+    S.K.load_row(7, r7);
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        D.y_old[i] = S.K[7][i];
-        const double k0 = S.K[0][i], k2 = S.K[2][i], k3 = S.K[3][i], k4 = S.K[4][i], k5 = S.K[5][i], k6 = S.K[6][i];
+        D.y_old[i] = r7[i];
+        const double k0 = r0[i], k2 = r2[i], k3 = r3[i], k4 = r4[i], k5 = r5[i], k6 = r6[i];
         D.Q[i][0] = k0;
         D.Q[i][1] = DP(p11) * k0 + DP(p13) * k2 + DP(p14) * k3 + DP(p15) * k4 + DP(p16) * k5 + DP(p17) * k6;
         D.Q[i][2] = DP(p21) * k0 + DP(p23) * k2 + DP(p24) * k3 + DP(p25) * k4 + DP(p26) * k5 + DP(p27) * k6;

@@ -14,8 +14,15 @@
 #include "ivp.cuh"
 #include "model.cuh"
 
-// 1: Runge-Kutta stage values of the hot kernel in shared memory instead of registers / local memory.  Measured equal
-// (25.9 vs 25.5 ms, DESIGN.md 6: the kernel is bound by L1 data-pipe wavefronts, and an LDS costs what an LDL costs)
+// 1: the throughput build of the free-arc kernel of GRIDDED fields runs the rolled step (rk45.cuh rk_step_rolled) with
+// the right-hand side inlined once and the Runge-Kutta stage values in shared memory.  0: the unrolled step with a called
+// right-hand side everywhere (round 1's kernel).  The latency builds (small batches, one extremal per warp) and analytic
+// fields always keep the unrolled step: they are bound by one thread's dependent chain, which the stage loop and the
+// shared-memory round trips lengthen (movor 28.7 -> 30.0 ms, Gyre 2.74 -> 2.87 ms with the rolled step).
+#ifndef DABRY_FAST_STEP
+#define DABRY_FAST_STEP 1
+#endif
+// 1: stage values of the unrolled step in shared memory too (measured equal in round 1: 25.9 vs 25.5 ms)
 #ifndef DABRY_K_IN_SHARED
 #define DABRY_K_IN_SHARED 0
 #endif
@@ -140,10 +147,10 @@ DABRY_HD void site_reset(const SiteStore& S, int s) {
 // ---------------------------------------------------------------------------------------------------------
 // integrate_site_to_target_index
 
-template <int FK>
+template <int FK, bool INLINED = false>
 struct AugRhs {
     const ProblemDev& P;
-    DABRY_HD void operator()(double t, const double* y, double* dy) const { rhs_aug<FK>(P, t, y, dy); }
+    DABRY_HD void operator()(double t, const double* y, double* dy) const { rhs_aug<FK, INLINED>(P, t, y, dy); }
 };
 
 template <int FK>
@@ -244,7 +251,7 @@ struct ConstrSink {
 //
 // Part A - the free arc (solver_ef.py:482-504): solve_ivp on the augmented system with the target / obstacle events.
 // A terminal obstacle event leaves the entry record (obstacle, t_enter_obs, index_t_obs, state at entry) for part B.
-template <int FK, int METHOD, bool CHUNKED>
+template <int FK, int METHOD, bool CHUNKED, bool FAST = false>
 DABRY_HD void site_free_arc(const ProblemDev& P, const SiteStore& S, int s, int index_t, unsigned& n_attempts,
                             unsigned& n_calls, int step_budget, double t_park = INFINITY, bool resume_only = false) {
     IvpCarry<4> carry;
@@ -278,22 +285,27 @@ DABRY_HD void site_free_arc(const ProblemDev& P, const SiteStore& S, int s, int 
     const Sample y0s = S.xp[S.at(s, idx0)];
     const double y0[4] = {y0s.x0, y0s.x1, y0s.p0, y0s.p1};
     const EvalGrid grid = make_eval_grid(S.times[idx0], S.times[index_t], n, 1);
-    AugRhs<FK> rhs{P};
+    // FAST: rolled step, right-hand side inlined once (Dormand-Prince only: RK4 has no stage table here)
+    constexpr bool kRolled = FAST && METHOD == METHOD_DOPRI5;
+    AugRhs<FK, kRolled> rhs{P};
     FreeEvents ev{P, S, s};
     FreeSink sink{P, S, s, idx0};
     IvpResult<4> res;
-#if defined(__CUDA_ARCH__) && DABRY_K_IN_SHARED
-    // the hot kernel keeps the stage values of the step in shared memory (rk45.cuh KShared): 32 KB per block
-    __shared__ double k_tile[8 * 4 * DABRY_FREE_ARC_THREADS];
-    solve_ivp<4, METHOD, KShared<4, DABRY_FREE_ARC_THREADS>>(
-        rhs, ev, sink, grid.at(0), grid.at(n - 1), y0, grid, P.max_step, P.rtol, P.atol, res, n_attempts,
-        CHUNKED ? &carry : nullptr, CHUNKED ? step_budget : 0, KShared<4, DABRY_FREE_ARC_THREADS>{k_tile + threadIdx.x},
-        t_park);
-#else
-    solve_ivp<4, METHOD, KRegisters<4>, (!CHUNKED && DABRY_DEFER_RETRY != 0)>(
-        rhs, ev, sink, grid.at(0), grid.at(n - 1), y0, grid, P.max_step, P.rtol, P.atol, res, n_attempts,
-        CHUNKED ? &carry : nullptr, CHUNKED ? step_budget : 0, KRegisters<4>(), t_park);
+#if defined(__CUDA_ARCH__)
+    if constexpr (FAST || DABRY_K_IN_SHARED != 0) {
+        // the stage values of the step live in shared memory (rk45.cuh KShared): 32 KB per block of 128 threads
+        __shared__ __align__(16) double k_tile[8 * 4 * DABRY_FREE_ARC_THREADS];
+        solve_ivp<4, METHOD, KShared<4, DABRY_FREE_ARC_THREADS>, false, kRolled>(
+            rhs, ev, sink, grid.at(0), grid.at(n - 1), y0, grid, P.max_step, P.rtol, P.atol, res, n_attempts,
+            CHUNKED ? &carry : nullptr, CHUNKED ? step_budget : 0,
+            KShared<4, DABRY_FREE_ARC_THREADS>{k_tile + 2 * threadIdx.x}, t_park);
+    } else
 #endif
+    {
+        solve_ivp<4, METHOD, KRegisters<4>, (!CHUNKED && DABRY_DEFER_RETRY != 0), kRolled>(
+            rhs, ev, sink, grid.at(0), grid.at(n - 1), y0, grid, P.max_step, P.rtol, P.atol, res, n_attempts,
+            CHUNKED ? &carry : nullptr, CHUNKED ? step_budget : 0, KRegisters<4>(), t_park);
+    }
     if (CHUNKED && res.status == IVP_DEFERRED) {  // nothing happened yet: a later window starts this arc afresh
         S.flags[s] |= SITE_DEFERRED;
         --n_calls;

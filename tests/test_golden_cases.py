@@ -90,6 +90,25 @@ def test_sites_auto_horizon_gpu(key, cuda_lib):
     _check_site_case(key, auto_horizon=True)
 
 
+# The throughput build of the free-arc kernel (gridded fields: rolled Dormand-Prince step, right-hand side inlined once,
+# stage values in shared memory - csrc/site.cuh DABRY_FAST_STEP) only runs for batches above 16 384 extremals; the golden
+# cases are far smaller, so these tests pin every batch to it (DABRY_B200_WIDE_BATCH=0) and repeat the exact comparison.
+FAST_STEP_CASES = ['era5_like_R', 'planar_waves_R', 'regional_constrained_R', 'regional_constrained_T']
+
+
+@pytest.mark.parametrize('key', FAST_STEP_CASES)
+def test_sites_throughput_build_hostsim(key, hostsim, monkeypatch):
+    monkeypatch.setenv('DABRY_B200_WIDE_BATCH', '0')
+    _check_site_case(key)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('key', FAST_STEP_CASES)
+def test_sites_throughput_build_gpu(key, cuda_lib, monkeypatch):
+    monkeypatch.setenv('DABRY_B200_WIDE_BATCH', '0')
+    _check_site_case(key)
+
+
 @pytest.mark.parametrize('key', SIMPLE_CASES)
 def test_simple_hostsim(key, hostsim):
     _check_simple_case(key)
