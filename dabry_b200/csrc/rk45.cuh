@@ -297,8 +297,10 @@ static const DormandPrinceRows h_dp_rows = DABRY_DP_ROWS_INIT;
 // DABRY_FAST_KEEP: what the rolled step keeps in registers besides shared memory - 1: K[0] (read by every stage),
 // 2: the row the last right-hand side produced (the last term of the next stage's sum), 4: the rows of the error estimate
 // for the interpolant of the accepted step (built inside the step instead of by rk_dense).
+// Measured (profiles/r02_ab_rolled.txt, free arcs of configs 4 / 4-fp32 / 3 / 5): 0: 24.70 / 21.29 / 14.06 / 17.45 ms,
+// 1: 24.55 / 21.37 / 14.40 / 17.46, 2: 24.31 / 21.29 / 13.54 / 17.34, 3: 24.50 / 21.62 / 14.45 / 17.35, 4: 26.1 (config 4).
 #ifndef DABRY_FAST_KEEP
-#define DABRY_FAST_KEEP 3
+#define DABRY_FAST_KEEP 2
 #endif
 // dense: when not null, the interpolant of the accepted step is built here, from the rows the error estimate has just
 // read (rk_dense would read the same six rows from shared memory again).
@@ -323,7 +325,6 @@ DABRY_HD int rk_step_rolled(RkState<N, KS>& S, const Rhs& rhs, double t_bound, d
         const double h = t_new - t;
         h_abs = fabs(h);
         ++n_attempts;
-#pragma unroll 1
         double ks[N];  // the row the last right-hand side produced
 #pragma unroll 1
         for (int s = 1; s <= 6; ++s) {
