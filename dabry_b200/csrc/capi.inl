@@ -93,8 +93,13 @@ int dabry_create(const dabry_config* c, dabry_solver** out) {
 
 void dabry_destroy(dabry_solver* h) {
     if (!h) return;
+    const bool timing = getenv("DABRY_B200_DEBUG_TIMING") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     if (h->eng) DABRY_BACKEND::destroy_locked(h->eng->be, [&] { delete h->eng; });
     delete h;
+    if (timing)
+        fprintf(stderr, "dabry_destroy: %.2f ms\n",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
 }
 
 const char* dabry_last_error(const dabry_solver* h) {

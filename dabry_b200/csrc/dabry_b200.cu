@@ -213,7 +213,11 @@ public:
 
     ~CudaBackend() {
         if (stream_) {
+            // DABRY_B200_DEBUG_TIMING=1: host wall time of the parts of the destructor on stderr (diagnostic)
+            const bool timing = getenv("DABRY_B200_DEBUG_TIMING") != nullptr;
+            const auto t0 = std::chrono::steady_clock::now();
             cudaStreamSynchronize(stream_);
+            const auto t1 = std::chrono::steady_clock::now();
             for (cudaEvent_t e : {ev0_, ev1_, tot0_, tot1_})
                 if (e) cudaEventDestroy(e);
             if (copy_stream_) {
@@ -226,10 +230,17 @@ public:
                 cudaEventDestroy(sp.first);
                 cudaEventDestroy(sp.second);
             }
+            const auto t2 = std::chrono::steady_clock::now();
             if (d_small_) cudaFreeAsync(d_small_, stream_);
             if (d_block_sum_) cudaFreeAsync(d_block_sum_, stream_);
             cudaStreamSynchronize(stream_);
+            const auto t3 = std::chrono::steady_clock::now();
             cudaStreamDestroy(stream_);
+            if (timing) {
+                const auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+                fprintf(stderr, "dabry backend close: sync %.2f ms, events / copy stream %.2f ms, frees + sync %.2f ms, stream %.2f ms\n",
+                        ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, std::chrono::steady_clock::now()));
+            }
         }
     }
 
