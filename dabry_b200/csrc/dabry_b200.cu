@@ -206,6 +206,44 @@ private:
     size_t limit_;
 };
 
+// ---- process-wide pool of streams and events ----------------------------------------------------------------------
+// The usual pattern is one handle per solve() call: creating and destroying two streams and a dozen events per solve is
+// 0.4 ms when all goes well and now and then 3 - 23 ms of driver housekeeping (profiles/r02_e2e_outliers.txt).  A closed
+// handle parks its (synchronised) streams and events here, the next handle on the same device takes them.  Parked sets
+// are never destroyed: at process exit the driver reclaims them, and a static destructor must not call into a runtime
+// that may already be gone.
+struct StreamSet {
+    static constexpr int kCopySlots = 8;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t copy_ev[kCopySlots] = {};
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans;
+};
+
+class StreamPool {
+public:
+    static StreamPool& instance() {
+        static StreamPool* pool = new StreamPool;  // leaked on purpose (see above)
+        return *pool;
+    }
+    bool take(int device, StreamSet& out) {
+        std::lock_guard<std::mutex> lock(mutex_);
+        std::vector<StreamSet>& v = sets_[device];
+        if (v.empty()) return false;
+        out = std::move(v.back());
+        v.pop_back();
+        return true;
+    }
+    void give(int device, StreamSet&& set) {
+        std::lock_guard<std::mutex> lock(mutex_);
+        sets_[device].push_back(std::move(set));
+    }
+
+private:
+    std::mutex mutex_;
+    std::map<int, std::vector<StreamSet>> sets_;
+};
+
 // ---- backend ------------------------------------------------------------------------------------------------
 class CudaBackend {
 public:
@@ -217,29 +255,27 @@ public:
             const bool timing = getenv("DABRY_B200_DEBUG_TIMING") != nullptr;
             const auto t0 = std::chrono::steady_clock::now();
             cudaStreamSynchronize(stream_);
+            if (copy_stream_) cudaStreamSynchronize(copy_stream_);
             const auto t1 = std::chrono::steady_clock::now();
-            for (cudaEvent_t e : {ev0_, ev1_, tot0_, tot1_})
-                if (e) cudaEventDestroy(e);
-            if (copy_stream_) {
-                cudaStreamSynchronize(copy_stream_);
-                for (cudaEvent_t e : copy_ev_)
-                    if (e) cudaEventDestroy(e);
-                cudaStreamDestroy(copy_stream_);
-            }
-            for (auto& sp : spans_) {
-                cudaEventDestroy(sp.first);
-                cudaEventDestroy(sp.second);
-            }
-            const auto t2 = std::chrono::steady_clock::now();
             if (d_small_) cudaFreeAsync(d_small_, stream_);
             if (d_block_sum_) cudaFreeAsync(d_block_sum_, stream_);
             cudaStreamSynchronize(stream_);
-            const auto t3 = std::chrono::steady_clock::now();
-            cudaStreamDestroy(stream_);
+            const auto t2 = std::chrono::steady_clock::now();
+            // streams and events go back to the process-wide pool (idle: both streams were just synchronised)
+            StreamSet set;
+            set.stream = stream_;
+            set.copy_stream = copy_stream_;
+            set.ev[0] = ev0_;
+            set.ev[1] = ev1_;
+            set.ev[2] = tot0_;
+            set.ev[3] = tot1_;
+            for (int i = 0; i < kCopySlots; ++i) set.copy_ev[i] = copy_ev_[i];
+            set.spans = std::move(spans_);
+            StreamPool::instance().give(device_, std::move(set));
             if (timing) {
                 const auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-                fprintf(stderr, "dabry backend close: sync %.2f ms, events / copy stream %.2f ms, frees + sync %.2f ms, stream %.2f ms\n",
-                        ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, std::chrono::steady_clock::now()));
+                fprintf(stderr, "dabry backend close: sync %.2f ms, frees + sync %.2f ms, park %.2f ms\n", ms(t0, t1), ms(t1, t2),
+                        ms(t2, std::chrono::steady_clock::now()));
             }
         }
     }
@@ -305,11 +341,24 @@ public:
         device_ = device;
         sm_count_ = sms;
         if (!chk(cudaSetDevice(device), "cudaSetDevice")) return false;
-        if (!chk(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
-        cudaEventCreate(&ev0_);
-        cudaEventCreate(&ev1_);
-        cudaEventCreate(&tot0_);
-        cudaEventCreate(&tot1_);
+        StreamSet set;
+        if (StreamPool::instance().take(device, set)) {  // streams and events of a closed handle on this device
+            stream_ = set.stream;
+            copy_stream_ = set.copy_stream;
+            ev0_ = set.ev[0];
+            ev1_ = set.ev[1];
+            tot0_ = set.ev[2];
+            tot1_ = set.ev[3];
+            for (int i = 0; i < kCopySlots; ++i) copy_ev_[i] = set.copy_ev[i];
+            spans_ = std::move(set.spans);
+            span_used_ = 0;
+        } else {
+            if (!chk(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
+            cudaEventCreate(&ev0_);
+            cudaEventCreate(&ev1_);
+            cudaEventCreate(&tot0_);
+            cudaEventCreate(&tot1_);
+        }
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
             unsigned long long keep = ~0ull;
@@ -392,7 +441,7 @@ public:
         chk(cudaStreamSynchronize(stream_), "H2D sync");
     }
     // background H2D copy of one chunk on the copy stream; wait_chunk orders the compute stream behind it
-    static constexpr int kCopySlots = 8;
+    static constexpr int kCopySlots = StreamSet::kCopySlots;
     void upload_chunk_async(void* d, const void* h, size_t bytes, int slot) {
         if (!copy_stream_) {
             if (!chk(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking), "cudaStreamCreate")) return;
