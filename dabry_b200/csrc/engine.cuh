@@ -26,6 +26,9 @@
 #ifndef DABRY_FREE_CHUNK
 #define DABRY_FREE_CHUNK 0
 #endif
+#ifndef DABRY_GRID_GROUPS  // > 0: fixed number of groups of time frames of the streamed grid upload (0: by frame count)
+#define DABRY_GRID_GROUPS 0
+#endif
 #ifndef DABRY_INTEGRATE_MIN_BLOCKS
 #define DABRY_INTEGRATE_MIN_BLOCKS 4
 #endif
@@ -703,7 +706,7 @@ public:
         // alive and unchanged until that solve (or any other call that needs the whole grid) returns.
         // (only grids whose copy takes longer than the extra launches of the windows cost: 64 MB is 1.3 ms of PCIe)
         const bool big = stream_upload > 1 || sizeof(double) * 2 * (size_t) nodes >= ((size_t) 64 << 20);
-        const bool streamed = world == 1 && stream_upload && big && unsteady && !grad && nt >= 2 * kGridGroups &&
+        const bool streamed = world == 1 && stream_upload && big && unsteady && !grad && nt >= 4 &&
                               (!w || w->scale_time > 0.) && be.host_is_pinned(values);
         if (world > 1) {
             const int64_t first = share * comm_rank();
@@ -737,8 +740,14 @@ public:
         P.field.kind = f32 ? FIELD_GRID_F32 : FIELD_GRID;
         set_wrapper(w);
         if (streamed) {
-            const int per = (nt + kGridGroups - 1) / kGridGroups;
-            for (int g = 0; g < kGridGroups; ++g) group_frames[g] = imin((g + 1) * per, nt);
+            // about eight time frames per group: every group costs a window of the free arcs (a relaunch of every arc and
+            // its tail, ~1 ms), the first group is waited for (0.36 ms per frame at the PCIe rate).  Measured with 3 / 4 / 5 /
+            // 6 groups: 34.9 / 35.9 / 37.1 / 39.3 ms per end-to-end solve for config 4 (24 frames), 37.3 / 36.5 / 36.1 / 36.1
+            // for config 3 (48 frames) - profiles/r02_ab_e2e_groups.txt.  DABRY_GRID_GROUPS > 0 fixes the number.
+            n_groups = DABRY_GRID_GROUPS > 0 ? DABRY_GRID_GROUPS : imax(2, imin(kMaxGridGroups, (nt + 4) / 8));
+            if (n_groups > nt / 2) n_groups = imax(1, nt / 2);
+            const int per = (nt + n_groups - 1) / n_groups;
+            for (int g = 0; g < n_groups; ++g) group_frames[g] = imin((g + 1) * per, nt);
             pending_pack = ph;
             pending_values = d_values;
             pending_host = values;
@@ -768,10 +777,7 @@ public:
     }
 
     // ---- streamed grid upload ----
-#ifndef DABRY_GRID_GROUPS
-#define DABRY_GRID_GROUPS 4
-#endif
-    static constexpr int kGridGroups = DABRY_GRID_GROUPS;
+    static constexpr int kMaxGridGroups = 8;  // = the copy-event slots of the backend
     void drop_pending_grid() {  // a handle destroyed or re-loaded while its grid is still arriving
         if (!grid_pending) return;
         be.sync_copies();
@@ -784,7 +790,7 @@ public:
     // pack the record frames whose two value frames have arrived with group `upto` (record frame f = k + 1 holds value
     // frames max(k, 0) and min(k + 1, nt - 1)); after the last group: max |w|, staging buffer released
     void issue_group() {  // background copy of the next group of value frames
-        if (groups_issued >= kGridGroups) return;
+        if (groups_issued >= n_groups) return;
         const GridDesc& G = P.field.grid;
         const int g = groups_issued++;
         const int f0 = g == 0 ? 0 : group_frames[g - 1], f1 = group_frames[g];
@@ -795,7 +801,7 @@ public:
     }
     void pack_groups(int upto) {
         const GridDesc& G = P.field.grid;
-        for (; groups_packed <= upto && groups_packed < kGridGroups; ++groups_packed) {
+        for (; groups_packed <= upto && groups_packed < n_groups; ++groups_packed) {
             const int have = group_frames[groups_packed];  // value frames 0 .. have - 1 are on the device after this group
             while (groups_issued <= groups_packed) issue_group();
             be.wait_chunk(groups_packed);
@@ -808,7 +814,7 @@ public:
                 frames_packed = hi;
             }
         }
-        if (groups_packed >= kGridGroups && grid_pending) {
+        if (groups_packed >= n_groups && grid_pending) {
             unsigned long long key = 0;
             be.download(&key, pending_key, sizeof(key));
             memcpy(&flow_max_norm, &key, sizeof(key));
@@ -821,7 +827,7 @@ public:
         }
     }
     void finish_grid() {
-        if (grid_pending) pack_groups(kGridGroups - 1);
+        if (grid_pending) pack_groups(n_groups - 1);
     }
     // solver time before which every right-hand side of a step only touches value frames 0 .. have - 1
     double park_time(int have) const {
@@ -1435,7 +1441,7 @@ private:
     // streamed grid upload (set_flow_grid / pack_groups / integrate); DABRY_B200_STREAM_UPLOAD=0 disables it
     int stream_upload = 1;  // 0: never, 1: grids of 64 MB and more, 2: every eligible grid (tests)
     bool grid_pending = false;
-    int groups_packed = 0, frames_packed = 0, group_frames[kGridGroups] = {};
+    int n_groups = 4, groups_packed = 0, frames_packed = 0, group_frames[kMaxGridGroups] = {};
     PackGridPhase pending_pack{};
     double* pending_values = nullptr;
     const double* pending_host = nullptr;
