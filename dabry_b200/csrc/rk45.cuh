@@ -302,6 +302,9 @@ static const DormandPrinceRows h_dp_rows = DABRY_DP_ROWS_INIT;
 #ifndef DABRY_FAST_KEEP
 #define DABRY_FAST_KEEP 2
 #endif
+#ifndef DABRY_FAST_UNROLL_J  // 1: the row loads of a stage unrolled and predicated instead of a loop over the rows
+#define DABRY_FAST_UNROLL_J 0  // measured: configs 4 / 4-fp32 / 3 / 5 free arcs 24.55 / 21.05 / 13.43 / 17.17 ms vs 24.32 / 21.31 / 13.56 / 17.28
+#endif
 // dense: when not null, the interpolant of the accepted step is built here, from the rows the error estimate has just
 // read (rk_dense would read the same six rows from shared memory again).
 template <int N, class KS, class Rhs>
@@ -341,6 +344,19 @@ DABRY_HD int rk_step_rolled(RkState<N, KS>& S, const Rhs& rhs, double t_bound, d
                 for (int i = 0; i < N; ++i) acc[i] = DPR.a[s - 1][0] * r0[i];
             }
             const int j_end = (DABRY_FAST_KEEP & 2) ? s - 1 : s;  // the last term comes from registers
+#if DABRY_FAST_UNROLL_J
+            // the row loads of a stage issued together, predicated on the stage index, instead of a loop over j
+#pragma unroll
+            for (int j = 1; j < 6; ++j) {
+                if (j < j_end) {
+                    const double a = DPR.a[s - 1][j];
+                    double kj[N];
+                    S.K.load_row(j, kj);
+#pragma unroll
+                    for (int i = 0; i < N; ++i) acc[i] = acc[i] + a * kj[i];
+                }
+            }
+#else
 #pragma unroll 1
             for (int j = 1; j < j_end; ++j) {
                 const double a = DPR.a[s - 1][j];
@@ -349,6 +365,7 @@ DABRY_HD int rk_step_rolled(RkState<N, KS>& S, const Rhs& rhs, double t_bound, d
 #pragma unroll
                 for (int i = 0; i < N; ++i) acc[i] = acc[i] + a * kj[i];
             }
+#endif
             if ((DABRY_FAST_KEEP & 2) && s >= 2) {
                 const double a = DPR.a[s - 1][s - 1];
 #pragma unroll
