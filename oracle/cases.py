@@ -49,11 +49,33 @@ CASES['regional_constrained_T'] = _case('regional_constrained_T', 'synthetic', '
                                         gen_args=(9, 91, 51), solver_kwargs=dict(max_depth=8))
 
 
+# Fields of the catalogue that no CI case of the reference uses (flowfield.py:906-973): a radial Gauss outflow whose
+# centre, radius and strength are tabulated in time, over a uniform cross flow.  `api.flowfield` is the flowfield module
+# of the reference or of this package.
+def _radial_gauss_t_problem(api):
+    F = api.flowfield
+    nt = 6
+    center = np.column_stack((np.linspace(0.35, 0.65, nt), np.linspace(0.7, 0.3, nt)))
+    ff = F.RadialGaussFFT(center, np.linspace(0.15, 0.3, nt), np.linspace(0.5, 0.7, nt), np.linspace(0.3, 0.6, nt),
+                          t_end=1.2, t_start=0.1) + F.UniformFF(np.array((0.1, -0.15)))
+    return api.NavigationProblem(ff, np.array((0.1, 0.5)), np.array((0.9, 0.5)), 1., bl=np.array((0., 0.)),
+                                 tr=np.array((1., 1.)), name='radial_gauss_t')
+
+
+ANALYTIC = {'radial_gauss_t': _radial_gauss_t_problem}
+CASES['radial_gauss_t_R'] = _case('radial_gauss_t_R', 'analytic', 'R', build='radial_gauss_t',
+                                  solver_kwargs=dict(max_depth=6), total_duration=1.5)
+CASES['radial_gauss_t_T'] = _case('radial_gauss_t_T', 'analytic', 'T', build='radial_gauss_t',
+                                  solver_kwargs=dict(max_depth=6), total_duration=1.5)
+
+
 def build_problem(case, api):
     """``api`` needs: NavigationProblem, DiscreteFF, Coords, CircleObs, CirclePenalty (DiscretePenalty for the case that
     uses one)."""
     if case.kind == 'catalog':
         return api.NavigationProblem.from_name(case.name).rescale()
+    if case.kind == 'analytic':
+        return ANALYTIC[case.build](api).rescale()
     from dabry_b200 import synthetic
     sc = getattr(synthetic, case.gen)(*case.gen_args)
     coords = api.Coords.GCS if sc.coords == 'gcs' else api.Coords.CARTESIAN
@@ -75,6 +97,9 @@ def solver_args(case, pb):
     kwargs = dict(case.solver_kwargs)
     if case.kind == 'catalog' and case.name in TIME_BOUND:
         return (pb, TIME_BOUND[case.name]), kwargs
+    if case.kind == 'analytic':
+        # the horizon in the rescaled clock of the problem (rescale() divides times by length_reference / srf)
+        return (pb, case.total_duration), kwargs
     if case.kind == 'synthetic':
         from dabry_b200 import synthetic
         sc_td = getattr(synthetic, case.gen)(2, 4, 4).total_duration

@@ -31,7 +31,8 @@ def reference_api():
     from dabry.misc import Coords
     from dabry.obstacle import CircleObs
     from dabry.penalty import CirclePenalty, DiscretePenalty
-    return SimpleNamespace(NavigationProblem=NavigationProblem, DiscreteFF=DiscreteFF, Coords=Coords,
+    import dabry.flowfield as flowfield
+    return SimpleNamespace(flowfield=flowfield, NavigationProblem=NavigationProblem, DiscreteFF=DiscreteFF, Coords=Coords,
                            CircleObs=CircleObs, CirclePenalty=CirclePenalty, DiscretePenalty=DiscretePenalty,
                            SolverEFResampling=sef.SolverEFResampling, SolverEFTrimming=sef.SolverEFTrimming,
                            SolverEFSimple=sef.SolverEFSimple, sef=sef)

@@ -30,7 +30,8 @@ def package_api():
     from dabry_b200.misc import Coords
     from dabry_b200.obstacle import CircleObs
     from dabry_b200.penalty import CirclePenalty, DiscretePenalty
-    return SimpleNamespace(NavigationProblem=NavigationProblem, DiscreteFF=DiscreteFF, Coords=Coords,
+    import dabry_b200.flowfield as flowfield
+    return SimpleNamespace(flowfield=flowfield, NavigationProblem=NavigationProblem, DiscreteFF=DiscreteFF, Coords=Coords,
                            CircleObs=CircleObs, CirclePenalty=CirclePenalty, DiscretePenalty=DiscretePenalty,
                            SolverEFResampling=sef.SolverEFResampling, SolverEFTrimming=sef.SolverEFTrimming,
                            SolverEFSimple=sef.SolverEFSimple)
