@@ -189,9 +189,12 @@ struct FreeArcPhase {  // the hot kernel: one thread per extremal, free arc with
 #ifndef DABRY_SPREAD_BATCH  // work items up to which an arc kernel runs one extremal per warp
 #define DABRY_SPREAD_BATCH 2048
 #endif
+#ifndef DABRY_SPREAD_THREADS  // warps of a block of the one-extremal-per-warp launch share the instruction cache of an SM
+#define DABRY_SPREAD_THREADS 32
+#endif
 template <class Phase>
 struct Spread {
-    static constexpr int kThreads = 32;
+    static constexpr int kThreads = DABRY_SPREAD_THREADS;
     static constexpr int kMinBlocks = 1;
     Phase inner;
     DABRY_HD void operator()(int64_t i) const {
